@@ -1,0 +1,200 @@
+/*
+ * b200nuts.h -- C ABI of the B200-native NUTS/HMC engine (libb200nuts.so).
+ *
+ * This is the drop-in boundary for ONE hot path of pymc-devs/pymc:
+ *     model.logp_dlogp_function  evaluated inside  CpuLeapfrogIntegrator.step  under  NUTS._build_tree.
+ * The reference has no C API (it is pure Python); every entry point below cites the Python
+ * interface it replaces.  Host bindings are plain ctypes (pymc_b200/_lib.py); INTEGRATION.md shows
+ * the reference-side shim a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - every function returns 0 on success, <0 on failure; b200_last_error() gives the message
+ *     (thread-local).  No exception crosses the ABI.
+ *   - NUMERICAL failures are not errors: a non-finite energy inside a trajectory is a divergence
+ *     recorded per chain/draw in the stats (reference: IntegrationError -> divergence,
+ *     hmc/integration.py:95-107, hmc/nuts.py:399-440); a non-finite energy at the START of a draw
+ *     ("Bad initial energy", hmc/base_hmc.py:205-224) freezes that chain and sets its
+ *     bad_energy flag -- the host wrapper raises SamplingError like the reference.
+ *   - the caller owns every input/output buffer.  Each call states whether its pointers are host
+ *     or device memory via `B200_MEM_HOST` / `B200_MEM_DEVICE`; host buffers are staged
+ *     through pinned memory inside the call.
+ *   - a handle is bound to the CUDA device that was current at creation and is not thread-safe
+ *     (one process per GPU; the reference isolates chains in processes, sampling/parallel.py).
+ *   - all floating point is IEEE fp64, like the reference's floatX=float64 default.
+ */
+#ifndef B200NUTS_H
+#define B200NUTS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NUTS_VERSION 100 /* 0.1.0 */
+
+/* memory space of caller-provided buffers */
+#define B200_MEM_HOST 0
+#define B200_MEM_DEVICE 1
+
+/* model kinds: the hand-written fused logp+gradient device functions (csrc/models.cuh).
+ * Each replaces the compiled PyTensor callable built at pymc/model/core.py:232-267 for that model. */
+#define B200_MODEL_STD_NORMAL 0    /* x ~ Normal(0,1)^n                           (test model)      */
+#define B200_MODEL_EIGHT_SCHOOLS 1 /* BASELINE config 1, q = [mu, log tau, theta_t[J]]              */
+#define B200_MODEL_RADON 2         /* BASELINE config 2, benchmarks/benchmarks/benchmarks.py:26-46  */
+#define B200_MODEL_LOGISTIC 3      /* BASELINE config 3, beta~N(0,1), y~Bernoulli(logit_p=X beta)   */
+#define B200_MODEL_STOCHVOL 4      /* BASELINE config 4, AR(1) stochastic volatility               */
+#define B200_MODEL_MVGAUSS 5       /* BASELINE config 5, x~MvNormal(0, chol=L), dense mass matrix   */
+
+/* mass-matrix kinds (reference: pymc/step_methods/hmc/quadpotential.py) */
+#define B200_MASS_DIAG 0       /* QuadPotentialDiag      :582-630  (fixed diagonal)                   */
+#define B200_MASS_DIAG_ADAPT 1 /* QuadPotentialDiagAdapt :211-355  (per-chain Welford windows)        */
+#define B200_MASS_DENSE 2      /* QuadPotentialFull      :680-725  (fixed dense covariance)           */
+
+/* where the momentum noise z ~ N(0,I) of `potential.random()` (quadpotential.py:323-326) comes from */
+#define B200_MOMENTUM_DEVICE_PHILOX 0 /* generated on device: Philox4x32-10 + Box-Muller, keyed per chain   */
+#define B200_MOMENTUM_HOST_BUFFER 1   /* caller supplies z[C][T][n] (e.g. NumPy Generator.normal: draw-parity) */
+
+typedef struct b200_model b200_model; /* opaque: model constants + observed data resident in HBM */
+
+/* What Model.logp_dlogp_function closes over: the model kind, the raveled size n and the observed
+ * data (pymc/model/core.py:464-529).  Unused fields are 0/NULL.  All pointers are HOST memory; the
+ * data is copied (and re-laid-out for coalesced access) into device memory by b200_model_create. */
+typedef struct b200_model_desc {
+    int32_t kind;        /* B200_MODEL_*                                                              */
+    int32_t n;           /* length of the raveled unconstrained vector q                              */
+    int64_t n_obs;       /* RADON: observations; LOGISTIC: rows; STOCHVOL: T; EIGHT_SCHOOLS: J        */
+    int32_t n_groups;    /* RADON: counties                                                           */
+    const double* x;     /* RADON: floor[n_obs]; LOGISTIC: X[n_obs][n] row-major; MVGAUSS: prec[n][n]  */
+    const double* y;     /* RADON/STOCHVOL/EIGHT_SCHOOLS: y[n_obs]                                     */
+    const double* aux;   /* EIGHT_SCHOOLS: sigma[J]; MVGAUSS: cov[n][n] (dense mass matrix)           */
+    const int32_t* idx;  /* RADON: county_idx[n_obs] in [0, n_groups)                                 */
+    const uint8_t* y_u8; /* LOGISTIC: y[n_obs] in {0,1}                                               */
+    double scalar0;      /* MVGAUSS: sum(log diag L) (constant of the log-density)                    */
+} b200_model_desc;
+
+/* NumPy PCG64 stream state (numpy.random.PCG64().state["state"]): 128-bit LCG state and increment.
+ * One `step` stream per chain (tree direction / multinomial picks, reference order: SURVEY 8a a15). */
+typedef struct b200_pcg64 {
+    uint64_t state_hi, state_lo;
+    uint64_t inc_hi, inc_lo;
+} b200_pcg64;
+
+/* Sampler configuration: the keyword surface of pm.NUTS / BaseHMC (hmc/nuts.py:132, hmc/base_hmc.py:82-98). */
+typedef struct b200_nuts_cfg {
+    int32_t chains;              /* C: independent chains in this call                                */
+    int32_t tune;                /* warm-up iterations (adaptation on)                                */
+    int32_t draws;               /* iterations after stop_tuning()                                    */
+    int32_t max_treedepth;       /* default 10                                                        */
+    int32_t early_max_treedepth; /* default 8: used while tuning and iter_count < 200                 */
+    int32_t adapt_step_size;     /* default 1                                                         */
+    int32_t mass_kind;           /* B200_MASS_*                                                       */
+    int32_t momentum_source;     /* B200_MOMENTUM_*                                                   */
+    int32_t store_warmup;        /* 1: outputs hold tune+draws iterations; 0: only the `draws` part   */
+    int32_t reserved0;
+    double step_scale;           /* default 0.25; eps0 = step_scale / n**0.25 (base_hmc.py:161)       */
+    double target_accept;        /* default 0.8                                                       */
+    double gamma;                /* default 0.05                                                      */
+    double k;                    /* default 0.75                                                      */
+    double t0;                   /* default 10                                                        */
+    double Emax;                 /* default 1000                                                      */
+    /* QuadPotentialDiagAdapt parameters (quadpotential.py:216-229; init_nuts uses weight 10) */
+    double mass_initial_weight;  /* default 10                                                        */
+    int32_t adaptation_window;   /* default 101                                                       */
+    int32_t discard_window;      /* default 50                                                        */
+    uint64_t philox_seed;        /* key for B200_MOMENTUM_DEVICE_PHILOX                               */
+} b200_nuts_cfg;
+
+/* Per-draw sampler statistics, struct-of-arrays [C][T] with T = store_warmup ? tune+draws : draws.
+ * Names follow NUTS.stats_dtypes_shapes (hmc/nuts.py:110-130).  Any pointer may be NULL (not recorded).
+ * All pointers live in the memory space given by `mem`. */
+typedef struct b200_stats {
+    int32_t* depth;
+    int32_t* tree_size;            /* == n_proposals == leapfrog gradient evaluations of the draw     */
+    int32_t* index_in_trajectory;
+    uint8_t* diverging;
+    uint8_t* reached_max_treedepth;
+    double* step_size;
+    double* step_size_bar;
+    double* mean_tree_accept;
+    double* energy;
+    double* energy_error;
+    double* max_energy_error;
+    double* model_logp;
+} b200_stats;
+
+/* Per-chain end-of-run state, arrays of length C (any pointer may be NULL). */
+typedef struct b200_chain_summary {
+    int64_t* grad_evals;     /* total logp+grad evaluations incl. the one at the start of every draw  */
+    int32_t* bad_energy_at;  /* -1, or the iteration at which "Bad initial energy" froze the chain    */
+    double* final_step_size; /* exp(log_bar) after tuning                                            */
+    double* final_var;       /* [C][n] diagonal inverse-mass ("_var") at the end of the run           */
+} b200_chain_summary;
+
+int b200_version(void);
+const char* b200_last_error(void);
+
+/* Number of visible CUDA devices (0 if none / no driver): lets a host binding fail loudly. */
+int b200_device_count(void);
+/* Binds the calling thread to a device (cudaSetDevice).  One process per GPU. */
+int b200_set_device(int device);
+
+/* Replaces: Model.logp_dlogp_function(ravel_inputs=True) -> ValueGradFunction
+ *           (pymc/model/core.py:464-529, :142-305) -- the compile step. */
+int b200_model_create(const b200_model_desc* desc, b200_model** out);
+void b200_model_destroy(b200_model* model);
+int b200_model_n(const b200_model* model);
+
+/* Replaces: ValueGradFunction._pytensor_function(q) -> (logp, dlogp), batched over C points
+ *           (built pymc/model/core.py:232-267; called hmc/integration.py:51-52,70,129).
+ * q[C][n] row-major, logp[C], grad[C][n]; `mem` is B200_MEM_HOST or B200_MEM_DEVICE for all three. */
+int b200_logp_dlogp(b200_model* model, const double* q, int32_t C, double* logp, double* grad,
+                    int32_t mem, void* stream);
+
+/* Replaces: CpuLeapfrogIntegrator.compute_state + n_steps x CpuLeapfrogIntegrator._step with a
+ *           diagonal potential (hmc/integration.py:68-75, :109-145; quadpotential.py:610-630).
+ * In/out (struct-of-arrays, one row per chain): q,p,v,grad [C][n]; energy, logp [C]; idx [C].
+ * var[C][n] is the diagonal inverse mass, eps[C] the signed step size.  If n_steps == 0 only the
+ * start state (grad, v, energy, logp) is computed from (q, p). */
+int b200_leapfrog(b200_model* model, const double* var, const double* eps, int32_t n_steps,
+                  int32_t C, double* q, double* p, double* v, double* grad, double* energy,
+                  double* logp, int64_t* idx, int32_t mem, void* stream);
+
+/* Replaces the whole multi-chain sampling loop for NUTS:
+ *   _sample_many/_mp_sample/_iter_sample   pymc/sampling/mcmc.py:1385-1583   (chains x iterations)
+ *   BaseHMC.astep                          hmc/base_hmc.py:196-288           (one draw)
+ *   NUTS._hamiltonian_step / _Tree         hmc/nuts.py:204-489               (tree doubling, U-turn, picks)
+ *   CpuLeapfrogIntegrator                  hmc/integration.py:68-145         (leapfrog)
+ *   QuadPotentialDiag(Adapt)               hmc/quadpotential.py:211-355,582-630
+ *   DualAverageAdaptation                  pymc/step_methods/step_sizes.py:41-84
+ * All chains run inside one persistent kernel; there is no host round-trip per leapfrog or per draw.
+ *
+ *   q0[C][n]          start points (unconstrained)
+ *   var0[C][n]        initial diagonal inverse mass (ones for jitter+adapt_diag); NULL = ones
+ *   mean0[C][n]       DIAG_ADAPT: initial mean of the foreground estimator (init_nuts passes the mean
+ *                     start point over chains, mcmc.py:1890); NULL = zeros
+ *   rng[C]            per-chain NumPy PCG64 `step` stream states; updated in place on return
+ *   z[C][Ttot][n]     momentum noise when momentum_source == B200_MOMENTUM_HOST_BUFFER, else NULL
+ *   draws_out[C][T][n]  accepted positions (unconstrained), T per `store_warmup`
+ *   stats, summary    see above; their pointers are in the same memory space
+ *   mem               memory space of ALL the buffers above
+ */
+int b200_nuts_run(b200_model* model, const b200_nuts_cfg* cfg, const double* q0, const double* var0,
+                  const double* mean0, b200_pcg64* rng, const double* z, double* draws_out,
+                  const b200_stats* stats, const b200_chain_summary* summary, int32_t mem,
+                  void* stream);
+
+/* Device time (ms, CUDA events on the launching stream) and launch count of the kernels of the
+ * most recent b200_nuts_run / b200_logp_dlogp / b200_leapfrog call on this thread. */
+int b200_last_kernel_ms(double* ms, int32_t* launches);
+
+/* fp64 FMA micro-benchmark: sustained DFMA throughput in TFLOP/s of this device (roofline
+ * denominator for compute-bound configs; MEASURED_PEAKS.json has only HBM and bf16). */
+int b200_measure_fp64_tflops(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NUTS_H */

@@ -1,0 +1,117 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own NUTS code (loaded verbatim from
+/root/reference by oracle/ref_loader.py) on the NumPy logp/grad restatement.
+
+Run in the builder container only (the reference does not exist on the GPU box):
+
+    python -m oracle.make_golden
+
+Every file stores the inputs (start points, seeds, momentum noise z, mass matrix) next to the
+reference's outputs (accepted positions and the per-draw sampler stats of hmc/nuts.py:478-489),
+so tests can replay the exact case through oracle/nuts_numpy.py and through the CUDA engine.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import logp_numpy, ref_loader  # noqa: E402
+from pymc_b200 import models  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+STAT_KEYS = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_max_treedepth", "step_size",
+             "step_size_bar", "mean_tree_accept", "energy", "energy_error", "max_energy_error", "model_logp"]
+
+
+def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None):
+    """One chain through the verbatim reference.  adapt=True: DiagAdapt(mean=q0, ones, weight 10) + dual
+    averaging (what init_nuts builds, mcmc.py:1890-1894); adapt=False: fixed QuadPotentialDiag(var), fixed eps."""
+    f = logp_numpy.make_logp(spec)
+    qp = ref_loader.quadpotential()
+    n = spec.n
+    if adapt:
+        pot = qp.QuadPotentialDiagAdapt(n, q0.copy(), np.ones(n), 10)
+    else:
+        pot = qp.QuadPotentialDiag(np.ones(n) if var is None else np.asarray(var, dtype="d"))
+    start = {v.name: q0[v.offset : v.offset + v.size].copy() for v in spec.vars}
+    kw = dict(nuts_kwargs or {})
+    if eps is not None:
+        kw["step_scale"] = eps * n**0.25  # base_hmc.py:161 inverts to step_size == eps
+    step, _ = ref_loader.make_nuts(f, spec.var_sizes, start, potential=pot, step_rng=0, adapt_step_size=adapt, **kw)
+    step.setup_chain(np.random.default_rng(seed), tune, draws)
+    if tune == 0:
+        step.tune = False
+    pt, qs, sts = start, [], []
+    for i in range(tune + draws):
+        if i == tune:
+            step.stop_tuning()
+        pt, st = step.step(pt)
+        qs.append(np.concatenate([np.ravel(pt[v.name]) for v in spec.vars]))
+        sts.append(st[0])
+    stats = {k: np.array([s[k] for s in sts]) for k in STAT_KEYS}
+    final_var = np.array(step.potential._var if adapt else step.potential.v)
+    return np.array(qs), stats, final_var, float(step.step_size)
+
+
+def noise(seed, T, n):
+    """The momentum normals the reference's potential draws: setup_chain spawns the potential stream
+    from the chain stream (base_hmc.py:300-302), then one normal(size=n) per draw (quadpotential.py:325,:619)."""
+    g = np.random.default_rng(seed).spawn(1)[0]
+    return np.array([g.normal(size=n) for _ in range(T)])
+
+
+def case(name, spec_name, spec_args, q0s, seeds, *, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None):
+    spec = models.BUILDERS[spec_name](**spec_args)
+    C = len(seeds)
+    Q, ST, FV, FE, Z = [], [], [], [], []
+    for c in range(C):
+        v = None if var is None else var[c]
+        e = None if eps is None else float(eps[c])
+        q, st, fv, fe = run_reference(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, adapt=adapt, var=v,
+                                      eps=e, nuts_kwargs=nuts_kwargs)
+        Q.append(q); ST.append(st); FV.append(fv); FE.append(fe)
+        Z.append(noise(seeds[c], tune + draws, spec.n))
+    out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, adapt=adapt, draws_q=np.array(Q),
+               z=np.array(Z), final_var=np.array(FV), final_step_size=np.array(FE),
+               var=np.array(var) if var is not None else np.ones((C, spec.n)),
+               eps=np.array(eps) if eps is not None else np.full(C, np.nan))
+    for k in STAT_KEYS:
+        out["stat_" + k] = np.array([s[k] for s in ST])
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    ts = out["stat_tree_size"]
+    print(f"{name}: {C} chains x {tune}+{draws}, grad evals {int(ts.sum())}, mean depth {out['stat_depth'].mean():.2f}, "
+          f"divergences {int(out['stat_diverging'].sum())}")
+    return out
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference not present; golden vectors can only be generated in the builder container")
+    # --- Eight Schools: the SURVEY 8c loader self-check case (start 0, unit mass, eps0, seed 20240922) ---
+    es = models.eight_schools()
+    case("eight_schools_fixed", "eight_schools", {}, [np.zeros(10)], [20240922], tune=0, draws=40, adapt=False)
+    rng = np.random.default_rng(11)
+    q0s = [es.initial_point() + rng.uniform(-1, 1, 10) for _ in range(3)]
+    case("eight_schools_adapt", "eight_schools", {}, q0s, [101, 102, 103], tune=300, draws=100, adapt=True)
+    # --- std normal n=100, fixed eps ---
+    q0s = [rng.standard_normal(100) for _ in range(2)]
+    case("std_normal_fixed", "std_normal", {"n": 100}, q0s, [7, 8], tune=0, draws=30, adapt=False)
+    # --- Radon: full adaptation from jittered starts, then a fixed-eps/fixed-mass replay from the warm state ---
+    rd = models.radon()
+    q0s = [rd.initial_point() + rng.uniform(-1, 1, rd.n) for _ in range(2)]
+    a = case("radon_adapt", "radon", {}, q0s, [201, 202], tune=400, draws=50, adapt=True)
+    warm_q = [a["draws_q"][c, -1] for c in range(2)]
+    case("radon_fixed", "radon", {}, warm_q, [301, 302], tune=0, draws=40, adapt=False, var=a["final_var"],
+         eps=a["final_step_size"])
+    # small ragged radon (counties with 1..n obs, fewer counties than lanes), early treedepth cap exercised
+    q0s = [np.zeros(2 * 7 + 5) + rng.uniform(-1, 1, 19)]
+    case("radon_small_adapt", "radon", {"n_obs": 40, "n_counties": 7, "seed": 5}, q0s, [401], tune=250, draws=50,
+         adapt=True, nuts_kwargs={"max_treedepth": 6, "early_max_treedepth": 4})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+"""ctypes binding of libb200nuts.so (C ABI declared in include/b200nuts.h).
+
+The library is the product: there is NO CPU fallback.  ``load()`` raises if the shared object is
+missing, and every compute entry point raises ``B200Error`` when no CUDA device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200nuts.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE = 0, 1, 2
+MOMENTUM_DEVICE_PHILOX, MOMENTUM_HOST_BUFFER = 0, 1
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n", C.c_int32),
+        ("n_obs", C.c_int64),
+        ("n_groups", C.c_int32),
+        ("x", C.c_void_p),
+        ("y", C.c_void_p),
+        ("aux", C.c_void_p),
+        ("idx", C.c_void_p),
+        ("y_u8", C.c_void_p),
+        ("scalar0", C.c_double),
+    ]
+
+
+class Pcg64State(C.Structure):
+    _fields_ = [("state_hi", C.c_uint64), ("state_lo", C.c_uint64), ("inc_hi", C.c_uint64), ("inc_lo", C.c_uint64)]
+
+
+PCG64_DTYPE = np.dtype([("state_hi", "<u8"), ("state_lo", "<u8"), ("inc_hi", "<u8"), ("inc_lo", "<u8")])
+
+
+class NutsCfg(C.Structure):
+    _fields_ = [
+        ("chains", C.c_int32),
+        ("tune", C.c_int32),
+        ("draws", C.c_int32),
+        ("max_treedepth", C.c_int32),
+        ("early_max_treedepth", C.c_int32),
+        ("adapt_step_size", C.c_int32),
+        ("mass_kind", C.c_int32),
+        ("momentum_source", C.c_int32),
+        ("store_warmup", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("step_scale", C.c_double),
+        ("target_accept", C.c_double),
+        ("gamma", C.c_double),
+        ("k", C.c_double),
+        ("t0", C.c_double),
+        ("Emax", C.c_double),
+        ("mass_initial_weight", C.c_double),
+        ("adaptation_window", C.c_int32),
+        ("discard_window", C.c_int32),
+        ("philox_seed", C.c_uint64),
+    ]
+
+
+STAT_FIELDS = [
+    ("depth", np.int32),
+    ("tree_size", np.int32),
+    ("index_in_trajectory", np.int32),
+    ("diverging", np.uint8),
+    ("reached_max_treedepth", np.uint8),
+    ("step_size", np.float64),
+    ("step_size_bar", np.float64),
+    ("mean_tree_accept", np.float64),
+    ("energy", np.float64),
+    ("energy_error", np.float64),
+    ("max_energy_error", np.float64),
+    ("model_logp", np.float64),
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _ in STAT_FIELDS]
+
+
+SUMMARY_FIELDS = [
+    ("grad_evals", np.int64),
+    ("bad_energy_at", np.int32),
+    ("final_step_size", np.float64),
+    ("final_var", np.float64),
+]
+
+
+class ChainSummary(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _ in SUMMARY_FIELDS]
+
+
+# every symbol include/b200nuts.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("b200_version", C.c_int, []),
+    ("b200_last_error", C.c_char_p, []),
+    ("b200_device_count", C.c_int, []),
+    ("b200_set_device", C.c_int, [C.c_int]),
+    ("b200_model_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
+    ("b200_model_destroy", None, [C.c_void_p]),
+    ("b200_model_n", C.c_int, [C.c_void_p]),
+    ("b200_logp_dlogp", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    (
+        "b200_leapfrog",
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p],
+    ),
+    (
+        "b200_nuts_run",
+        C.c_int,
+        [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 6 + [C.POINTER(Stats), C.POINTER(ChainSummary), C.c_int32, C.c_void_p],
+    ),
+    ("b200_last_kernel_ms", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    ("b200_measure_fp64_tflops", C.c_int, [C.POINTER(C.c_double)]),
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the engine; raises if it has not been built (run ``./build.sh`` or ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: build the CUDA engine first (./build.sh); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(load().b200_last_error().decode())
+
+
+def require_gpu() -> None:
+    if load().b200_device_count() < 1:
+        raise B200Error("no CUDA device visible: the B200 engine has no CPU fallback")
+
+
+def ptr(a) -> int | None:
+    """Raw address of a NumPy array or torch tensor (None passes NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch.Tensor
+
+
+def last_kernel_ms() -> tuple[float, int]:
+    ms, n = C.c_double(), C.c_int32()
+    load().b200_last_kernel_ms(C.byref(ms), C.byref(n))
+    return ms.value, n.value

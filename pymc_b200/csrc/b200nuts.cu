@@ -1,0 +1,527 @@
+// libb200nuts.so -- C ABI implementation (see include/b200nuts.h for the contract and the reference
+// interfaces each entry point replaces).  Host side: model preparation (data re-layout for coalesced,
+// lane-balanced access), staging of host buffers, kernel dispatch on (model kind, elements per lane).
+#include "../../include/b200nuts.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "models.cuh"
+#include "nuts_warp.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: no exception crosses the ABI
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local double g_last_ms = 0.0;
+static thread_local int g_last_launches = 0;
+
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                   \
+    } while (0)
+
+struct DevBuf {  // owning device allocation
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct b200_model {
+    int kind = 0, n = 0, device = 0;
+    std::vector<void*> owned;  // device allocations
+    StdNormalModel::Params std_normal{};
+    EightSchoolsModel::Params eight{};
+    RadonModel::Params radon{};
+    ~b200_model() { for (void* p : owned) cudaFree(p); }
+};
+
+template <class T>
+static int upload(b200_model* m, const std::vector<T>& h, const T** out) {
+    void* d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(T), 16)));
+    m->owned.push_back(d);
+    if (!h.empty()) CU(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(d);
+    return 0;
+}
+
+extern "C" int b200_version(void) { return B200NUTS_VERSION; }
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int b200_set_device(int device) {
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model creation: "compile" step.  Re-lays the observed data out for the device functions.
+// ------------------------------------------------------------------------------------------------
+static int prepare_radon(b200_model* m, const b200_model_desc* d) {
+    const int J = d->n_groups;
+    const long long N = d->n_obs;
+    if (J <= 0 || N <= 0 || !d->x || !d->y || !d->idx) return fail("radon: missing data");
+    if (d->n != 2 * J + 5) return fail("radon: n=%d but 2*n_groups+5=%d", d->n, 2 * J + 5);
+    if (J > 0xffff) return fail("radon: n_groups > 65535 unsupported");
+    std::vector<std::vector<int>> members(J);
+    for (long long i = 0; i < N; ++i) {
+        const int c = d->idx[i];
+        if (c < 0 || c >= J) return fail("radon: county_idx[%lld]=%d out of range", i, c);
+        members[c].push_back((int)i);
+    }
+    // longest-processing-time assignment of counties to the 32 lanes
+    std::vector<int> order(J);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return members[a].size() > members[b].size(); });
+    std::vector<std::vector<int>> lane_c(32);
+    std::vector<long long> load(32, 0);
+    std::vector<int> empty;
+    for (int c : order) {
+        if (members[c].empty()) { empty.push_back(c); continue; }
+        int best = 0;
+        for (int l = 1; l < 32; ++l)
+            if (load[l] < load[best]) best = l;
+        lane_c[best].push_back(c);
+        load[best] += (long long)members[c].size();
+    }
+    int K = 0, M = 1;
+    for (int l = 0; l < 32; ++l) {
+        K = std::max<int>(K, (int)load[l]);
+        M = std::max<int>(M, (int)lane_c[l].size());
+    }
+    if (K >= 0x7fff) return fail("radon: more than 32766 observations per lane unsupported");
+    std::vector<double2> xy((size_t)K * 32, make_double2(0.0, 0.0));
+    std::vector<int32_t> seg((size_t)(M + 1) * 32, 0);
+    for (int l = 0; l < 32; ++l) {
+        int k = 0;
+        for (size_t j = 0; j < lane_c[l].size(); ++j) {
+            const int c = lane_c[l][j];
+            for (int i : members[c]) xy[(size_t)(k++) * 32 + l] = make_double2(d->x[i], d->y[i]);
+            seg[j * 32 + l] = (k << 16) | c;
+        }
+        seg[(size_t)M * 32 + l] = k;  // observations walked by the lane
+    }
+    RadonModel::Params& P = m->radon;
+    P.K = K; P.M = M; P.J = J; P.n_obs = (int)N; P.E = (int)empty.size();
+    if (upload(m, xy, &P.xy)) return -1;
+    if (upload(m, seg, &P.seg)) return -1;
+    if (upload(m, empty, &P.empty)) return -1;
+    return 0;
+}
+
+static int prepare_eight(b200_model* m, const b200_model_desc* d) {
+    const int J = (int)d->n_obs;
+    if (J <= 0 || !d->y || !d->aux) return fail("eight_schools: missing data");
+    if (d->n != J + 2) return fail("eight_schools: n=%d but J+2=%d", d->n, J + 2);
+    std::vector<double> y(d->y, d->y + J), is2(J), ls(J);
+    for (int j = 0; j < J; ++j) {
+        if (!(d->aux[j] > 0)) return fail("eight_schools: sigma[%d] must be > 0", j);
+        is2[j] = 1.0 / (d->aux[j] * d->aux[j]);
+        ls[j] = std::log(d->aux[j]);
+    }
+    EightSchoolsModel::Params& P = m->eight;
+    P.J = J;
+    if (upload(m, y, &P.y)) return -1;
+    if (upload(m, is2, &P.inv_s2)) return -1;
+    if (upload(m, ls, &P.log_s)) return -1;
+    return 0;
+}
+
+extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) {
+    if (!desc || !out) return fail("b200_model_create: null argument");
+    if (desc->n <= 0) return fail("b200_model_create: n must be positive");
+    if (b200_device_count() == 0) return fail("b200_model_create: no CUDA device visible");
+    b200_model* m = new b200_model();
+    m->kind = desc->kind;
+    m->n = desc->n;
+    cudaGetDevice(&m->device);
+    int rc = 0;
+    switch (desc->kind) {
+        case B200_MODEL_STD_NORMAL: m->std_normal.n = desc->n; break;
+        case B200_MODEL_EIGHT_SCHOOLS: rc = prepare_eight(m, desc); break;
+        case B200_MODEL_RADON: rc = prepare_radon(m, desc); break;
+        default: rc = fail("b200_model_create: model kind %d not implemented", desc->kind);
+    }
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void b200_model_destroy(b200_model* m) { delete m; }
+extern "C" int b200_model_n(const b200_model* m) { return m ? m->n : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------------------
+static int npl_for(int n) {
+    const int need = (n + 31) / 32;
+    const int opts[] = {1, 2, 4, 6, 8};
+    for (int o : opts)
+        if (need <= o) return o;
+    return 0;
+}
+
+// Calls f.template operator()<Model, NPL>(params) for the model's kind and size.
+template <class F>
+static int dispatch(const b200_model* m, F&& f) {
+    const int npl = npl_for(m->n);
+    if (!npl) return fail("n=%d exceeds the warp-team limit (256); block-team kernels not built for this model", m->n);
+#define B200_CASE_NPL(MODEL, PARAMS)                                          \
+    switch (npl) {                                                            \
+        case 1: return f.template operator()<MODEL, 1>(PARAMS);               \
+        case 2: return f.template operator()<MODEL, 2>(PARAMS);               \
+        case 4: return f.template operator()<MODEL, 4>(PARAMS);               \
+        case 6: return f.template operator()<MODEL, 6>(PARAMS);               \
+        default: return f.template operator()<MODEL, 8>(PARAMS);              \
+    }
+    switch (m->kind) {
+        case B200_MODEL_STD_NORMAL: B200_CASE_NPL(StdNormalModel, m->std_normal)
+        case B200_MODEL_EIGHT_SCHOOLS: B200_CASE_NPL(EightSchoolsModel, m->eight)
+        case B200_MODEL_RADON: B200_CASE_NPL(RadonModel, m->radon)
+    }
+#undef B200_CASE_NPL
+    return fail("dispatch: model kind %d not implemented", m->kind);
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t s_) : s(s_) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+    }
+    void stop(int launches) {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        g_last_ms = ms;
+        g_last_launches = launches;
+    }
+    ~Timer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// Host<->device staging of one array.
+struct Staged {
+    DevBuf dev;
+    void* user = nullptr;
+    size_t bytes = 0;
+    bool host = false, out = false;
+    void* ptr() const { return host ? dev.p : user; }
+};
+static int stage_in(Staged& s, const void* user, size_t bytes, int mem, bool copy_in, bool copy_out,
+                    cudaStream_t st) {
+    s.user = const_cast<void*>(user);
+    s.bytes = bytes;
+    s.host = (mem == B200_MEM_HOST) && user != nullptr;
+    s.out = copy_out;
+    if (s.host) {
+        CU(s.dev.alloc(bytes));
+        if (copy_in) CU(cudaMemcpyAsync(s.dev.p, user, bytes, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+static int stage_out(Staged& s, cudaStream_t st) {
+    if (s.host && s.out) CU(cudaMemcpyAsync(s.user, s.dev.p, s.bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// b200_logp_dlogp
+// ------------------------------------------------------------------------------------------------
+struct LogpLaunch {
+    const b200_model* m; int C; const double* q; double* logp; double* grad; cudaStream_t st;
+    template <class Model, int NPL>
+    int operator()(const typename Model::Params& MP) const {
+        const int wpb = 8;
+        const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
+        const size_t smem = data + (size_t)wpb * 2 * 32 * NPL * sizeof(double);
+        auto kern = logp_grad_warp_kernel<Model, NPL>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
+        kern<<<blocks, wpb * 32, smem, st>>>(MP, m->n, C, q, logp, grad);
+        CU(cudaGetLastError());
+        return 0;
+    }
+};
+
+extern "C" int b200_logp_dlogp(b200_model* m, const double* q, int32_t C, double* logp, double* grad,
+                               int32_t mem, void* stream) {
+    if (!m || !q || !logp || !grad) return fail("b200_logp_dlogp: null argument");
+    if (C <= 0) return 0;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t vb = (size_t)C * m->n * sizeof(double);
+    Staged sq, sl, sg;
+    if (stage_in(sq, q, vb, mem, true, false, st)) return -1;
+    if (stage_in(sl, logp, (size_t)C * sizeof(double), mem, false, true, st)) return -1;
+    if (stage_in(sg, grad, vb, mem, false, true, st)) return -1;
+    Timer t(st);
+    LogpLaunch L{m, C, (const double*)sq.ptr(), (double*)sl.ptr(), (double*)sg.ptr(), st};
+    if (dispatch(m, L)) return -1;
+    t.stop(1);
+    if (stage_out(sl, st) || stage_out(sg, st)) return -1;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// b200_leapfrog
+// ------------------------------------------------------------------------------------------------
+struct LeapLaunch {
+    const b200_model* m; int C, n_steps; const double *var, *eps; double *q, *p, *v, *grad, *energy, *logp;
+    long long* idx; cudaStream_t st;
+    template <class Model, int NPL>
+    int operator()(const typename Model::Params& MP) const {
+        const int wpb = 8;
+        const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
+        const size_t smem = data + (size_t)wpb * 2 * 32 * NPL * sizeof(double);
+        auto kern = leapfrog_warp_kernel<Model, NPL>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
+        kern<<<blocks, wpb * 32, smem, st>>>(MP, m->n, C, var, eps, n_steps, q, p, v, grad, energy, logp, idx);
+        CU(cudaGetLastError());
+        return 0;
+    }
+};
+
+extern "C" int b200_leapfrog(b200_model* m, const double* var, const double* eps, int32_t n_steps, int32_t C,
+                             double* q, double* p, double* v, double* grad, double* energy, double* logp,
+                             int64_t* idx, int32_t mem, void* stream) {
+    if (!m || !var || !eps || !q || !p || !v || !grad || !energy || !logp || !idx)
+        return fail("b200_leapfrog: null argument");
+    if (n_steps < 0) return fail("b200_leapfrog: n_steps < 0");
+    if (C <= 0) return 0;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t vb = (size_t)C * m->n * sizeof(double), sb = (size_t)C * sizeof(double);
+    Staged s_var, s_eps, s_q, s_p, s_v, s_g, s_e, s_l, s_i;
+    if (stage_in(s_var, var, vb, mem, true, false, st) || stage_in(s_eps, eps, sb, mem, true, false, st) ||
+        stage_in(s_q, q, vb, mem, true, true, st) || stage_in(s_p, p, vb, mem, true, true, st) ||
+        stage_in(s_v, v, vb, mem, true, true, st) || stage_in(s_g, grad, vb, mem, true, true, st) ||
+        stage_in(s_e, energy, sb, mem, true, true, st) || stage_in(s_l, logp, sb, mem, true, true, st) ||
+        stage_in(s_i, idx, (size_t)C * sizeof(int64_t), mem, true, true, st))
+        return -1;
+    Timer t(st);
+    LeapLaunch L{m, C, n_steps, (const double*)s_var.ptr(), (const double*)s_eps.ptr(), (double*)s_q.ptr(),
+                 (double*)s_p.ptr(), (double*)s_v.ptr(), (double*)s_g.ptr(), (double*)s_e.ptr(),
+                 (double*)s_l.ptr(), (long long*)s_i.ptr(), st};
+    if (dispatch(m, L)) return -1;
+    t.stop(1);
+    if (stage_out(s_q, st) || stage_out(s_p, st) || stage_out(s_v, st) || stage_out(s_g, st) ||
+        stage_out(s_e, st) || stage_out(s_l, st) || stage_out(s_i, st))
+        return -1;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// b200_nuts_run
+// ------------------------------------------------------------------------------------------------
+struct NutsLaunch {
+    const b200_model* m; NutsDev P; cudaStream_t st;
+    template <class Model, int NPL>
+    int operator()(const typename Model::Params& MP) {
+        constexpr int NP = 32 * NPL;
+        int wpb = env_int("B200_NUTS_WPB", 4);
+        int hot = env_int("B200_NUTS_HOT", 2);
+        wpb = std::max(1, std::min(wpb, 8));
+        hot = std::max(0, std::min(hot, P.max_td));
+        const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
+        size_t smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot);
+        while (smem > 227 * 1024 && hot > 0) {  // shrink the hot window until the CTA fits
+            --hot;
+            smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot);
+        }
+        if (smem > 227 * 1024) return fail("nuts: shared memory request %zu B exceeds 227 KB", smem);
+        P.hot_levels = hot;
+        DevBuf scratch;
+        P.scratch_stride = nuts_scratch_doubles(NP, P.max_td);
+        CU(scratch.alloc((size_t)P.C * P.scratch_stride * sizeof(double)));
+        P.scratch = scratch.as<double>();
+        auto kern = nuts_warp_kernel<Model, NPL>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int blocks = (P.C + wpb - 1) / wpb;
+        Timer t(st);
+        kern<<<blocks, wpb * 32, smem, st>>>(P, MP);
+        CU(cudaGetLastError());
+        t.stop(1);
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        return 0;
+    }
+};
+
+extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const double* q0, const double* var0,
+                             const double* mean0, b200_pcg64* rng, const double* z, double* draws_out,
+                             const b200_stats* stats, const b200_chain_summary* summary, int32_t mem,
+                             void* stream) {
+    if (!m || !cfg || !q0 || !rng || !draws_out) return fail("b200_nuts_run: null argument");
+    const int C = cfg->chains, n = m->n;
+    if (C <= 0) return fail("b200_nuts_run: chains must be positive");
+    if (cfg->tune < 0 || cfg->draws < 0 || cfg->tune + cfg->draws <= 0) return fail("b200_nuts_run: bad tune/draws");
+    if (cfg->max_treedepth < 1 || cfg->max_treedepth > kMaxLevels || cfg->early_max_treedepth < 1 ||
+        cfg->early_max_treedepth > cfg->max_treedepth)
+        return fail("b200_nuts_run: treedepth must satisfy 1 <= early <= max <= %d", kMaxLevels);
+    if (cfg->mass_kind != B200_MASS_DIAG && cfg->mass_kind != B200_MASS_DIAG_ADAPT)
+        return fail("b200_nuts_run: mass kind %d not implemented for this model", cfg->mass_kind);
+    if (cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER && !z)
+        return fail("b200_nuts_run: momentum_source=HOST_BUFFER but z is null");
+    if (!(cfg->step_scale > 0)) return fail("b200_nuts_run: step_scale must be > 0");
+    if (cfg->adaptation_window < 1) return fail("b200_nuts_run: adaptation_window must be >= 1");
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const long long Ttot = (long long)cfg->tune + cfg->draws;
+    const long long T = cfg->store_warmup ? Ttot : cfg->draws;
+    const size_t vb = (size_t)C * n * sizeof(double);
+    Staged s_q0, s_var0, s_mean0, s_rng, s_z, s_draws;
+    if (stage_in(s_q0, q0, vb, mem, true, false, st) || stage_in(s_var0, var0, vb, mem, true, false, st) ||
+        stage_in(s_mean0, mean0, vb, mem, true, false, st) ||
+        stage_in(s_rng, rng, (size_t)C * sizeof(b200_pcg64), mem, true, true, st) ||
+        stage_in(s_z, cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER ? z : nullptr, vb * Ttot, mem, true, false, st) ||
+        stage_in(s_draws, draws_out, vb * T, mem, false, true, st))
+        return -1;
+    // stats / summary arrays
+    b200_stats ds{};
+    b200_chain_summary dsum{};
+    Staged st_arr[12], sm_arr[4];
+    const size_t ct = (size_t)C * T;
+    if (stats) {
+#define B200_ST(i, field, type)                                                              \
+    if (stats->field) {                                                                      \
+        if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st)) return -1; \
+        ds.field = (type*)st_arr[i].ptr();                                                   \
+    }
+        B200_ST(0, depth, int32_t) B200_ST(1, tree_size, int32_t) B200_ST(2, index_in_trajectory, int32_t)
+        B200_ST(3, diverging, uint8_t) B200_ST(4, reached_max_treedepth, uint8_t) B200_ST(5, step_size, double)
+        B200_ST(6, step_size_bar, double) B200_ST(7, mean_tree_accept, double) B200_ST(8, energy, double)
+        B200_ST(9, energy_error, double) B200_ST(10, max_energy_error, double) B200_ST(11, model_logp, double)
+#undef B200_ST
+    }
+    if (summary) {
+        if (summary->grad_evals) {
+            if (stage_in(sm_arr[0], summary->grad_evals, (size_t)C * sizeof(int64_t), mem, false, true, st)) return -1;
+            dsum.grad_evals = (int64_t*)sm_arr[0].ptr();
+        }
+        if (summary->bad_energy_at) {
+            if (stage_in(sm_arr[1], summary->bad_energy_at, (size_t)C * sizeof(int32_t), mem, false, true, st)) return -1;
+            dsum.bad_energy_at = (int32_t*)sm_arr[1].ptr();
+        }
+        if (summary->final_step_size) {
+            if (stage_in(sm_arr[2], summary->final_step_size, (size_t)C * sizeof(double), mem, false, true, st)) return -1;
+            dsum.final_step_size = (double*)sm_arr[2].ptr();
+        }
+        if (summary->final_var) {
+            if (stage_in(sm_arr[3], summary->final_var, vb, mem, false, true, st)) return -1;
+            dsum.final_var = (double*)sm_arr[3].ptr();
+        }
+    }
+    // outputs of frozen chains ("bad initial energy") stay NaN
+    if (s_draws.host) CU(cudaMemsetAsync(s_draws.ptr(), 0xff, vb * T, st));
+
+    NutsDev P{};
+    P.C = C; P.n = n; P.tune = cfg->tune; P.draws = cfg->draws;
+    P.max_td = cfg->max_treedepth; P.early_td = cfg->early_max_treedepth;
+    P.adapt_step = cfg->adapt_step_size; P.mass_kind = cfg->mass_kind;
+    P.momentum_source = cfg->momentum_source; P.store_warmup = cfg->store_warmup;
+    P.window = cfg->adaptation_window; P.discard = cfg->discard_window;
+    P.eps0 = cfg->step_scale / std::pow((double)n, 0.25);  // base_hmc.py:161
+    P.target = cfg->target_accept; P.gamma = cfg->gamma; P.kappa = cfg->k; P.t0 = cfg->t0;
+    P.Emax = cfg->Emax; P.init_weight = cfg->mass_initial_weight;
+    P.philox_seed = cfg->philox_seed;
+    P.q0 = (const double*)s_q0.ptr(); P.var0 = (const double*)s_var0.ptr();
+    P.mean0 = (const double*)s_mean0.ptr(); P.z = (const double*)s_z.ptr();
+    P.rng = (b200_pcg64*)s_rng.ptr(); P.draws_out = (double*)s_draws.ptr();
+    P.st = ds; P.sm = dsum;
+
+    NutsLaunch L{m, P, st};
+    if (dispatch(m, L)) return -1;
+
+    if (stage_out(s_rng, st) || stage_out(s_draws, st)) return -1;
+    for (auto& s : st_arr) if (stage_out(s, st)) return -1;
+    for (auto& s : sm_arr) if (stage_out(s, st)) return -1;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int b200_last_kernel_ms(double* ms, int32_t* launches) {
+    if (ms) *ms = g_last_ms;
+    if (launches) *launches = g_last_launches;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 FMA peak micro-benchmark
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int b200_measure_fp64_tflops(double* tflops) {
+    if (!tflops) return fail("null argument");
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    DevBuf out;
+    CU(out.alloc((size_t)blocks * threads * sizeof(double)));
+    dfma_peak_kernel<<<blocks, threads>>>(out.as<double>(), 64);
+    CU(cudaDeviceSynchronize());
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        Timer t(0);
+        dfma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
+        CU(cudaGetLastError());
+        t.stop(1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, flops / (g_last_ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,110 @@
+// Shared device helpers: team (warp / block) reductions, libm-shaped scalar functions, bulk-TMA staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define B200_FULL_MASK 0xffffffffu
+
+#ifndef B200_HALF_LOG_2PI
+#define B200_HALF_LOG_2PI 0.91893853320467274178032973640562
+#endif
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// scalar helpers (same branch structure as the NumPy functions the reference calls)
+// ---------------------------------------------------------------------------------------------
+// numpy.logaddexp (npy_logaddexp): used at hmc/nuts.py:415,376,465
+__device__ __forceinline__ double logaddexp(double x, double y) {
+    if (x == y) return x + 0.69314718055994530942;  // log 2
+    const double d = x - y;
+    if (d > 0) return x + log1p(exp(-d));
+    if (d <= 0) return y + log1p(exp(d));
+    return x + y;  // NaN
+}
+
+__device__ __forceinline__ double softplus(double x) {
+    return fmax(x, 0.0) + log1p(exp(-fabs(x)));
+}
+
+__device__ __forceinline__ double sigmoid(double x) {
+    const double e = exp(-fabs(x));
+    const double r = 1.0 / (1.0 + e);
+    return x >= 0 ? r : e * r;
+}
+
+// Normal(0,1) log-density constant part is added by callers; this is the HalfCauchy(beta) density of
+// x = exp(z) plus the log-transform Jacobian (+z), and its derivative in z.
+// Reference: Cauchy.logp continuous.py:2287-2288, HalfCauchy.logp :2383-2385, LogTransform
+// logprob/transforms.py:880-891.  `x` must be exp(z) (passed in so callers can share the exp).
+__device__ __forceinline__ void halfcauchy_log(double z, double x, double beta, double log_beta,
+                                               double& val, double& dz) {
+    const double t = x / beta;
+    const double u = t * t;
+    val = (0.69314718055994530942 - 1.1447298858494001741 /* log pi */) - log_beta - log1p(u) + z;
+    dz = 1.0 - 2.0 * u / (1.0 + u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp team: one chain = one warp; lane l owns elements l, l+32, ...  All reductions are xor
+// butterflies, so every lane ends with bit-identical results (commutativity of IEEE add) and all
+// tree decisions are warp-uniform without a broadcast.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(B200_FULL_MASK, x, o);
+    return x;
+}
+
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&x)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] += __shfl_xor_sync(B200_FULL_MASK, x[i], o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk TMA (cp.async.bulk, SASS UBLKCP): stage a contiguous global array into shared memory,
+// completion signalled on an mbarrier.  bytes must be a multiple of 16, both addresses 16B aligned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+}  // namespace b200

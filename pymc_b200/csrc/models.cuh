@@ -1,0 +1,212 @@
+// Hand-written fused log-density + reverse-mode gradient device functions, one per model kind.
+//
+// Each `*Model::eval` replaces ONE call of the compiled PyTensor function
+//     ValueGradFunction._pytensor_function(q) -> (logp, dlogp)
+// (built at pymc/model/core.py:232-267, called at hmc/integration.py:52,70,129) for a chain owned by a
+// WARP: q lives in the warp's shared-memory slice `q_s` (padded to NP = 32*NPL, pad = 0), the gradient
+// is written to `g_s`, and logp is returned warp-uniform (xor-butterfly reductions).
+// The math restates the reference densities (cited per model) with the gradients of SURVEY.md
+// Appendix C; bad parameters cannot occur because scale parameters are exp() of unconstrained values.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// x ~ Normal(0,1)^n  (test model; Normal.logp distributions/continuous.py:526-527)
+// ------------------------------------------------------------------------------------------------
+struct StdNormalModel {
+    struct Params {
+        int n;
+    };
+    __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
+    __device__ static void stage(const Params&, char*, uint64_t*) {}
+    template <int NPL>
+    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            const double x = q_s[i];
+            s = fma(x, x, s);
+            g_s[i] = -x;
+        }
+        s = warp_sum(s);
+        return -0.5 * s - P.n * B200_HALF_LOG_2PI;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Eight Schools, non-centred (BASELINE config 1).  q = [mu, log tau, theta_t[J]]
+//   mu~Normal(0,5); tau~HalfCauchy(5) (log transform); theta_t~Normal(0,1); y_j~Normal(mu+tau*theta_t_j, sigma_j)
+// Densities: Normal continuous.py:526-527; HalfCauchy :2383-2385 (+Cauchy :2287-2288); log transform
+// + Jacobian logprob/transforms.py:880-891.  Gradient: SURVEY Appendix C-1.
+// ------------------------------------------------------------------------------------------------
+struct EightSchoolsModel {
+    struct Params {
+        const double* y;       // [J]
+        const double* inv_s2;  // [J] 1/sigma^2
+        const double* log_s;   // [J] log sigma
+        int J;
+    };
+    __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
+    __device__ static void stage(const Params&, char*, uint64_t*) {}
+    template <int NPL>
+    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane) {
+        const double mu = q_s[0], ltau = q_s[1];
+        const double tau = exp(ltau);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum r, sum r*tt, sum tt^2, sum loglik (w/o const)
+        for (int j = lane; j < P.J; j += 32) {
+            const double tt = q_s[2 + j];
+            const double th = fma(tau, tt, mu);
+            const double d = P.y[j] - th;
+            const double r = d * P.inv_s2[j];
+            acc[0] += r;
+            acc[1] = fma(r, tt, acc[1]);
+            acc[2] = fma(tt, tt, acc[2]);
+            acc[3] += -0.5 * d * r - P.log_s[j];
+            g_s[2 + j] = fma(tau, r, -tt);
+        }
+        warp_sum_n(acc);
+        double hc, dhc;
+        halfcauchy_log(ltau, tau, 5.0, 1.6094379124341002818 /* log 5 */, hc, dhc);
+        if (lane == 0) {
+            g_s[0] = -mu * (1.0 / 25.0) + acc[0];
+            g_s[1] = fma(tau, acc[1], dhc);
+        }
+        const double z = mu * 0.2;
+        const double lp_mu = -0.5 * z * z - B200_HALF_LOG_2PI - 1.6094379124341002818;
+        return lp_mu + hc + (-0.5 * acc[2] - P.J * B200_HALF_LOG_2PI) + (acc[3] - P.J * B200_HALF_LOG_2PI);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Radon hierarchical regression (BASELINE config 2; model benchmarks/benchmarks/benchmarks.py:34-45)
+//   q = [mu_a, log sigma_a, mu_b, log sigma_b, a[J], b[J], log eps]
+//   alpha_c = mu_a + sigma_a a_c ; beta_c = mu_b + sigma_b b_c ; y_i ~ Normal(alpha_c(i) + beta_c(i) x_i, eps)
+//   mu_* ~ Normal(0, 100**2) ; sigma_*, eps ~ HalfCauchy(5) ; a, b ~ Normal(0,1)
+// Gradient: SURVEY Appendix C-2.  The per-county segmented sums G_alpha, G_beta are the per-chain
+// reduction: observations are grouped by county at model-create time and counties are dealt to
+// the 32 lanes by longest-processing-time so every lane walks ~n_obs/32 observations; a lane keeps
+// its county's (alpha, beta, G_alpha, G_beta) in registers and finishes that county's two gradient
+// entries itself when the county ends.  The (x, y) pairs are an ELL array [K][32] of double2 staged
+// once per CTA into shared memory by bulk TMA and shared by all the CTA's chains.
+// ------------------------------------------------------------------------------------------------
+struct RadonModel {
+    struct Params {
+        const double2* xy;   // [K][32]  (floor_i, y_i) in lane-major ELL order
+        const int32_t* seg;  // [M][32]  (end_k << 16) | county   (end_k = one past the county's last k)
+                             // row M of seg: observations walked by each lane
+        const int32_t* empty;  // [E] counties without observations (prior terms only)
+        int K, M, J, n_obs, E;
+    };
+    __host__ __device__ static size_t xy_bytes(const Params& P) { return (size_t)P.K * 32 * sizeof(double2); }
+    __host__ __device__ static size_t seg_bytes(const Params& P) { return (size_t)(P.M + 1) * 32 * sizeof(int32_t); }
+    __host__ __device__ static size_t shared_bytes(const Params& P) { return xy_bytes(P) + seg_bytes(P); }
+
+    // CTA-wide: thread 0 issues two bulk-TMA copies (xy, then seg+tot which are contiguous in HBM).
+    __device__ static void stage(const Params& P, char* smem, uint64_t* bar) {
+        if (threadIdx.x == 0) {
+            const uint32_t b0 = (uint32_t)xy_bytes(P), b1 = (uint32_t)seg_bytes(P);
+            mbar_expect_tx(bar, b0 + b1);
+            tma_bulk_g2s(smem, P.xy, b0, bar);
+            tma_bulk_g2s(smem + b0, P.seg, b1, bar);
+        }
+    }
+
+    template <int NPL>
+    __device__ static double eval(const Params& P, const char* smem, const double* q_s, double* g_s, int lane) {
+        const double2* xy = reinterpret_cast<const double2*>(smem);
+        const int32_t* seg = reinterpret_cast<const int32_t*>(smem + xy_bytes(P));
+        const int J = P.J;
+        const double mu_a = q_s[0], mu_b = q_s[2];
+        // one exp() for the warp: lanes 0,1,2 take log sigma_a, log sigma_b, log eps
+        const int zi = (lane % 3 == 0) ? 1 : (lane % 3 == 1 ? 3 : 4 + 2 * J);
+        const double zl = q_s[zi];
+        const double ex = exp(zl);
+        // HalfCauchy(5)+Jacobian of the same three, one log1p() for the warp
+        double hc_l, dhc_l;
+        halfcauchy_log(zl, ex, 5.0, 1.6094379124341002818, hc_l, dhc_l);
+        const double sa = __shfl_sync(B200_FULL_MASK, ex, 0), sb = __shfl_sync(B200_FULL_MASK, ex, 1),
+                     eps = __shfl_sync(B200_FULL_MASK, ex, 2);
+        const double hca = __shfl_sync(B200_FULL_MASK, hc_l, 0), hcb = __shfl_sync(B200_FULL_MASK, hc_l, 1),
+                     hce = __shfl_sync(B200_FULL_MASK, hc_l, 2);
+        const double dhca = __shfl_sync(B200_FULL_MASK, dhc_l, 0), dhcb = __shfl_sync(B200_FULL_MASK, dhc_l, 1),
+                     dhce = __shfl_sync(B200_FULL_MASK, dhc_l, 2);
+        const double leps = q_s[4 + 2 * J];
+        const double inv_e2 = 1.0 / (eps * eps);
+        const double sa_ie2 = sa * inv_e2, sb_ie2 = sb * inv_e2;
+
+        // acc: S2, sum Ga, sum a*Ga, sum Gb, sum b*Gb, sum a^2, sum b^2   (Ga/Gb raw: sums of residuals)
+        double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const int total = seg[P.M * 32 + lane];
+        int j = 0;
+        int sg = seg[lane];
+        int end = sg >> 16, c = sg & 0xffff;
+        double a_c = 0.0, b_c = 0.0, al = 0.0, be = 0.0, Ga = 0.0, Gb = 0.0;
+        if (total > 0) {
+            a_c = q_s[4 + c];
+            b_c = q_s[4 + J + c];
+            al = fma(sa, a_c, mu_a);
+            be = fma(sb, b_c, mu_b);
+        }
+        for (int k = 0; k < P.K; ++k) {
+            if (k < total) {
+                const double2 d = xy[k * 32 + lane];
+                const double r = d.y - fma(be, d.x, al);
+                acc[0] = fma(r, r, acc[0]);
+                Ga += r;
+                Gb = fma(r, d.x, Gb);
+                if (k + 1 == end) {  // county finished: its two gradient entries are complete
+                    g_s[4 + c] = fma(sa_ie2, Ga, -a_c);
+                    g_s[4 + J + c] = fma(sb_ie2, Gb, -b_c);
+                    acc[1] += Ga;
+                    acc[2] = fma(a_c, Ga, acc[2]);
+                    acc[3] += Gb;
+                    acc[4] = fma(b_c, Gb, acc[4]);
+                    acc[5] = fma(a_c, a_c, acc[5]);
+                    acc[6] = fma(b_c, b_c, acc[6]);
+                    ++j;
+                    if (k + 1 < total) {
+                        sg = seg[j * 32 + lane];
+                        end = sg >> 16;
+                        c = sg & 0xffff;
+                        a_c = q_s[4 + c];
+                        b_c = q_s[4 + J + c];
+                        al = fma(sa, a_c, mu_a);
+                        be = fma(sb, b_c, mu_b);
+                        Ga = 0.0;
+                        Gb = 0.0;
+                    }
+                }
+            }
+        }
+        for (int e = lane; e < P.E; e += 32) {  // counties with no observations: prior terms only
+            const int ce = P.empty[e];
+            const double ae = q_s[4 + ce], bb = q_s[4 + J + ce];
+            g_s[4 + ce] = -ae;
+            g_s[4 + J + ce] = -bb;
+            acc[5] = fma(ae, ae, acc[5]);
+            acc[6] = fma(bb, bb, acc[6]);
+        }
+        warp_sum_n(acc);
+        const double S = 1.0e4;  // sigma = 100**2
+        if (lane == 0) {
+            g_s[0] = fma(inv_e2, acc[1], -mu_a * (1.0 / (S * S)));
+            g_s[1] = fma(sa_ie2, acc[2], dhca);
+            g_s[2] = fma(inv_e2, acc[3], -mu_b * (1.0 / (S * S)));
+            g_s[3] = fma(sb_ie2, acc[4], dhcb);
+            g_s[4 + 2 * J] = dhce + fma(acc[0], inv_e2, -(double)P.n_obs);
+        }
+        const double za = mu_a / S, zb = mu_b / S;
+        const double log_S = 9.2103403719761827361;  // log 1e4
+        double lp = (-0.5 * za * za - B200_HALF_LOG_2PI - log_S) + (-0.5 * zb * zb - B200_HALF_LOG_2PI - log_S);
+        lp += hca + hcb + hce;
+        lp += -0.5 * acc[5] - J * B200_HALF_LOG_2PI;
+        lp += -0.5 * acc[6] - J * B200_HALF_LOG_2PI;
+        lp += -0.5 * acc[0] * inv_e2 - P.n_obs * (B200_HALF_LOG_2PI + leps);
+        return lp;
+    }
+};
+
+}  // namespace b200

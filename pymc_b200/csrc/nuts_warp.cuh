@@ -1,0 +1,628 @@
+// The persistent NUTS kernel, chain = warp.
+//
+// One warp runs ONE chain for the whole run (tune + draws iterations) with no host round-trip:
+// momentum draw, start state, tree doubling with the generalised U-turn checks, multinomial picks,
+// dual-averaging step-size adaptation and the diagonal mass-matrix Welford windows all happen here.
+// It restates, operation by operation:
+//     BaseHMC.astep                hmc/base_hmc.py:196-288
+//     NUTS._hamiltonian_step       hmc/nuts.py:204-225
+//     _Tree.extend                 hmc/nuts.py:334-392
+//     _Tree._build_subtree         hmc/nuts.py:442-476   (recursion unrolled into a binary-counter stack)
+//     _Tree._single_step           hmc/nuts.py:394-440
+//     CpuLeapfrogIntegrator._step  hmc/integration.py:109-145
+//     QuadPotentialDiag(Adapt)     hmc/quadpotential.py:211-355, :582-630
+//     DualAverageAdaptation        step_sizes.py:41-84
+// and consumes the chain's NumPy PCG64 `step` stream in the reference order.
+//
+// Data placement (n <= 32*NPL, NP = 32*NPL, lane l owns elements l + 32k):
+//   registers : p (momentum of the integrator state), var (diag inverse mass), and the subtree under
+//               construction: left.p, p_sum, proposal q   -> 5*NPL doubles per lane
+//   shared    : q and grad of the integrator state (the model function needs all of q), the HOT lowest
+//               levels of the pending-subtree stack (level h is touched every 2^h leapfrogs), per-level
+//               scalars, and the model's observed data (staged once per CTA by bulk TMA)
+//   global/L2 : the colder stack levels, the main tree (both edge states, p_sum, proposal q) and the
+//               Welford accumulators -- touched once per doubling / per draw
+#pragma once
+#include "../../include/b200nuts.h"
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace b200 {
+
+constexpr int kMaxLevels = 12;  // pending-subtree levels (max_treedepth <= 12)
+
+struct NutsDev {
+    int C, n, tune, draws, max_td, early_td, adapt_step, mass_kind, momentum_source, store_warmup;
+    int window, discard, hot_levels;
+    double eps0, target, gamma, kappa, t0, Emax, init_weight;
+    unsigned long long philox_seed;
+    const double* q0;     // [C][n]
+    const double* var0;   // [C][n] or null
+    const double* mean0;  // [C][n] or null
+    const double* z;      // [C][Ttot][n] or null
+    b200_pcg64* rng;      // [C]
+    double* draws_out;    // [C][T][n]
+    b200_stats st;
+    b200_chain_summary sm;
+    double* scratch;            // per-chain global scratch
+    long long scratch_stride;   // doubles per chain
+};
+
+// global scratch layout per chain, in units of NP doubles
+enum { G_LQ = 0, G_LP, G_LG, G_RQ, G_RP, G_RG, G_PS, G_PQ, G_NEARP, G_FGM, G_FGV, G_BGM, G_BGV, G_STACK };
+
+__host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
+    return (long long)(G_STACK + 4 * levels) * NP;
+}
+// shared memory per warp (bytes): q, g, hot stack levels (level 0: 2 vectors, others: 4), scalars
+__host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot) {
+    const int vecs = 2 + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
+    return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double);
+}
+
+template <class Model, int NPL>
+__global__ void __launch_bounds__(256) nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
+    constexpr int NP = 32 * NPL;
+    extern __shared__ __align__(16) char smem_raw[];
+    __shared__ __align__(8) uint64_t tma_bar;
+
+    // ---- CTA prologue: stage the observed data into shared memory (bulk TMA) -------------------
+    const size_t data_bytes = (Model::shared_bytes(M) + 15) & ~(size_t)15;
+    if (data_bytes) {
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        Model::stage(M, smem_raw, &tma_bar);
+        mbar_wait(&tma_bar, 0);
+    }
+    const char* data_s = smem_raw;
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int chain = blockIdx.x * wpb + wib;
+    if (chain >= P.C) return;  // no CTA-wide barrier after this point
+
+    const int hot = P.hot_levels;
+    double* ws = reinterpret_cast<double*>(smem_raw + data_bytes + wib * nuts_warp_smem_bytes(NP, hot));
+    double* q_s = ws;
+    double* g_s = ws + NP;
+    double* hot_base = ws + 2 * NP;
+    double* sc_logw = hot_base + (hot > 0 ? 2 + 4 * (hot - 1) : 0) * NP;
+    double* sc_pe = sc_logw + kMaxLevels;
+    double* sc_plogp = sc_pe + kMaxLevels;
+    double* sc_pidx = sc_plogp + kMaxLevels;
+    double* gs = P.scratch + (long long)chain * P.scratch_stride;
+
+    // which: 0 = left.p, 1 = right.p, 2 = p_sum, 3 = proposal q.  Level 0 (a single leaf) keeps only 2, 3.
+    auto lvl = [&](int h, int which) -> double* {
+        if (h < hot) return hot_base + (h == 0 ? (which - 2) : (2 + 4 * (h - 1) + which)) * NP;
+        return gs + (long long)(G_STACK + 4 * h + which) * NP;
+    };
+    auto gvec = [&](int which) -> double* { return gs + (long long)which * NP; };
+
+    const int n = P.n;
+    const int Ttot = P.tune + P.draws;
+    const int T_out = P.store_warmup ? Ttot : P.draws;
+
+    // ---- per-chain persistent state ---------------------------------------------------------------
+    double var[NPL], p[NPL], lp[NPL], ps[NPL], pq[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+        const int i = lane + 32 * k;
+        q_s[i] = (i < n) ? P.q0[(long long)chain * n + i] : 0.0;
+        g_s[i] = 0.0;
+        var[k] = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
+        // Welford estimators: foreground starts at (mean0, var0 * weight, weight); background empty
+        if (P.mass_kind == B200_MASS_DIAG_ADAPT) {
+            gvec(G_FGM)[i] = (i < n && P.mean0) ? P.mean0[(long long)chain * n + i] : 0.0;
+            gvec(G_FGV)[i] = var[k] * P.init_weight;
+            gvec(G_BGM)[i] = 0.0;
+            gvec(G_BGV)[i] = 0.0;
+        }
+    }
+    int fg_m = G_FGM, fg_v = G_FGV, bg_m = G_BGM, bg_v = G_BGV;
+    double fg_n = P.init_weight, bg_n = 0.0;
+    int k_samples = 0, window = P.window;
+
+    // dual averaging (step_sizes.py:50-57)
+    double log_step = log(P.eps0), log_bar = log_step, hbar = 0.0;
+    const double da_mu = log(10.0 * P.eps0);
+    int da_count = 1;
+
+    Pcg64 rng;
+    {
+        const b200_pcg64 r = P.rng[chain];
+        rng.load(r.state_hi, r.state_lo, r.inc_hi, r.inc_lo);
+    }
+    long long n_grad = 0;
+    int bad_at = -1;
+    __syncwarp();
+
+    for (int it = 0; it < Ttot; ++it) {
+        const bool tuning = it < P.tune;
+        const bool adapting = tuning && P.adapt_step;
+
+        // ---- p0 = potential.random(): inv_std * z  (quadpotential.py:323-326, :617-619) ------------
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            double zz = 0.0;
+            if (i < n) {
+                zz = (P.momentum_source == B200_MOMENTUM_HOST_BUFFER)
+                         ? P.z[((long long)chain * Ttot + it) * n + i]
+                         : philox_normal(P.philox_seed, (uint32_t)chain, (uint32_t)it, (uint32_t)i);
+            }
+            p[k] = (1.0 / sqrt(var[k])) * zz;
+        }
+        // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
+        __syncwarp();
+        const double logp0 = Model::template eval<NPL>(M, data_s, q_s, g_s, lane);
+        __syncwarp();
+        ++n_grad;
+        double kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) kin = fma(p[k], var[k] * p[k], kin);
+        const double E0 = 0.5 * warp_sum(kin) - logp0;
+        if (!isfinite(E0)) {  // "Bad initial energy" (base_hmc.py:205-224): freeze the chain
+            bad_at = it;
+            break;
+        }
+        const double eps = exp(adapting ? log_step : log_bar);  // step_adapt.current (step_sizes.py:60-64)
+        const int maxd = (tuning && it < 200) ? P.early_td : P.max_td;  // nuts.py:205-208
+
+        // ---- _Tree.__init__ (nuts.py:292-332): both edges, proposal and p_sum are the start state ----
+        double* Lq = gvec(G_LQ); double* Lp = gvec(G_LP); double* Lg = gvec(G_LG);
+        double* Rq = gvec(G_RQ); double* Rp = gvec(G_RP); double* Rg = gvec(G_RG);
+        double* PS = gvec(G_PS); double* PQ = gvec(G_PQ); double* NEARP = gvec(G_NEARP);
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            const double qi = q_s[i], gi = g_s[i];
+            Lq[i] = qi; Rq[i] = qi; PQ[i] = qi;
+            Lg[i] = gi; Rg[i] = gi;
+            Lp[i] = p[k]; Rp[i] = p[k]; PS[i] = p[k];
+        }
+        int L_idx = 0, R_idx = 0;
+        double m_logw = 0.0, m_pe = E0, m_plogp = logp0;
+        int m_pidx = 0;
+        double log_accept = -INFINITY, max_de = 0.0;
+        int n_prop = 0, depth = 0;
+        bool diverged = false, turned = false, hit_max = false;
+
+        int d_iter = 0;
+        for (; d_iter < maxd; ++d_iter) {
+            const int dir = (rng.next_double() < 0.5) ? 1 : -1;  // nuts.py:215
+            // ---- load the edge we grow from into the integrator state; remember its p ----------------
+            const double* Eq = dir > 0 ? Rq : Lq;
+            const double* Ep = dir > 0 ? Rp : Lp;
+            const double* Eg = dir > 0 ? Rg : Lg;
+            int w_idx = dir > 0 ? R_idx : L_idx;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + 32 * k;
+                q_s[i] = Eq[i];
+                g_s[i] = Eg[i];
+                p[k] = Ep[i];
+                NEARP[i] = p[k];
+            }
+            const double es = dir * eps, dt = 0.5 * es;
+
+            // ---- _build_subtree(edge, depth, +-eps): 2^depth leaves, merges driven by a binary counter --
+            bool sub_div = false, sub_turn = false;
+            double c_logw = 0.0, c_pe = 0.0, c_plogp = 0.0;
+            int c_pidx = 0;
+            const int n_leaf = 1 << depth;
+            for (int leaf = 0; leaf < n_leaf; ++leaf) {
+                // -- one leapfrog (integration.py:109-145)
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    p[k] = fma(dt, g_s[i], p[k]);
+                    q_s[i] = fma(es, var[k] * p[k], q_s[i]);
+                }
+                __syncwarp();
+                const double logp = Model::template eval<NPL>(M, data_s, q_s, g_s, lane);
+                __syncwarp();
+                ++n_grad;
+                double kk = 0.0;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    p[k] = fma(dt, g_s[i], p[k]);
+                    kk = fma(p[k], var[k] * p[k], kk);
+                }
+                const double E = 0.5 * warp_sum(kk) - logp;
+                w_idx += dir;
+                // -- _single_step bookkeeping (nuts.py:406-440)
+                ++n_prop;
+                double dE = E - E0;
+                if (isnan(dE)) dE = INFINITY;
+                log_accept = logaddexp(log_accept, dE > 0 ? -dE : 0.0);
+                if (fabs(dE) > fabs(max_de)) max_de = dE;
+                if (!(dE < P.Emax)) {
+                    sub_div = true;
+                    break;
+                }
+                // the leaf as a height-0 subtree: left = right = p_sum = p, proposal = itself
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    lp[k] = p[k];
+                    ps[k] = p[k];
+                    pq[k] = q_s[lane + 32 * k];
+                }
+                c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
+
+                // -- merge with pending left siblings while the counter carries (nuts.py:452-476)
+                int h = 0;
+                for (int m = leaf; m & 1; m >>= 1, ++h) {
+                    const double* t_ps = lvl(h, 2);
+                    const double* t_lp = h ? lvl(h, 0) : t_ps;
+                    const double* t_rp = h ? lvl(h, 1) : t_ps;
+                    double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    if (h == 0) {
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) {
+                            const int i = lane + 32 * k;
+                            const double tp = t_ps[i];
+                            const double s = tp + ps[k];
+                            dots[0] = fma(s, var[k] * tp, dots[0]);
+                            dots[1] = fma(s, var[k] * p[k], dots[1]);
+                            lp[k] = tp;
+                            ps[k] = s;
+                        }
+                        dots[2] = dots[3] = dots[4] = dots[5] = 1.0;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) {
+                            const int i = lane + 32 * k;
+                            const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
+                            const double s = tp + ps[k];
+                            const double vl = var[k] * tl, vr = var[k] * p[k];
+                            dots[0] = fma(s, vl, dots[0]);
+                            dots[1] = fma(s, vr, dots[1]);
+                            const double s1 = tp + lp[k];  // tree1.p_sum + tree2.left.p
+                            dots[2] = fma(s1, vl, dots[2]);
+                            dots[3] = fma(s1, var[k] * lp[k], dots[3]);
+                            const double s2 = tr + ps[k];  // tree1.right.p + tree2.p_sum
+                            dots[4] = fma(s2, var[k] * tr, dots[4]);
+                            dots[5] = fma(s2, vr, dots[5]);
+                            lp[k] = tl;
+                            ps[k] = s;
+                        }
+                    }
+                    warp_sum_n(dots);
+                    const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
+                                      (dots[4] <= 0) || (dots[5] <= 0);
+                    const double t_logw = sc_logw[h];
+                    const double logw = logaddexp(t_logw, c_logw);
+                    const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
+                    if (!(log(u) < c_logw - logw)) {     // keep tree1's proposal
+                        const double* t_pq = lvl(h, 3);
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) pq[k] = t_pq[lane + 32 * k];
+                        c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
+                    }
+                    c_logw = logw;
+                    if (turn) {
+                        sub_turn = true;
+                        break;
+                    }
+                }
+                if (sub_turn) break;
+                // -- not the last leaf: park the subtree (height h) until its right sibling is built
+                if (leaf + 1 < n_leaf) {
+                    double* s_ps = lvl(h, 2);
+                    double* s_pq = lvl(h, 3);
+                    if (h == 0) {
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) {
+                            const int i = lane + 32 * k;
+                            s_ps[i] = ps[k];
+                            s_pq[i] = pq[k];
+                        }
+                    } else {
+                        double* s_lp = lvl(h, 0);
+                        double* s_rp = lvl(h, 1);
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) {
+                            const int i = lane + 32 * k;
+                            s_lp[i] = lp[k];
+                            s_rp[i] = p[k];
+                            s_ps[i] = ps[k];
+                            s_pq[i] = pq[k];
+                        }
+                    }
+                    if (lane == 0) {
+                        sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
+                    }
+                    __syncwarp();
+                }
+            }
+            ++depth;  // nuts.py:365 (counts the aborted doubling too)
+            if (sub_div || sub_turn) {
+                diverged = sub_div;
+                turned = sub_turn;
+                break;
+            }
+            // ---- the new outer edge is the integrator state (self.right/left = tree.right) ------------
+            {
+                double* Nq = dir > 0 ? Rq : Lq;
+                double* Np = dir > 0 ? Rp : Lp;
+                double* Ng = dir > 0 ? Rg : Lg;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    Nq[i] = q_s[i];
+                    Ng[i] = g_s[i];
+                    Np[i] = p[k];
+                }
+                if (dir > 0) R_idx = w_idx; else L_idx = w_idx;
+            }
+            // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
+            {
+                const double u = rng.next_double();
+                if (log(u) < c_logw - m_logw) {
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) PQ[lane + 32 * k] = pq[k];
+                    m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
+                }
+                m_logw = logaddexp(c_logw, m_logw);
+            }
+            // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
+            {
+                const double* FARP = dir > 0 ? Lp : Rp;
+                double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    const double so = PS[i], fp = FARP[i], np_ = NEARP[i];
+                    const double s = so + ps[k];
+                    PS[i] = s;
+                    const double vf = var[k] * fp, vw = var[k] * p[k];
+                    dots[0] = fma(s, vf, dots[0]);
+                    dots[1] = fma(s, vw, dots[1]);
+                    const double a = so + lp[k];   // old p_sum + (new subtree's edge adjacent to the old tree).p
+                    dots[2] = fma(a, vf, dots[2]);
+                    dots[3] = fma(a, var[k] * lp[k], dots[3]);
+                    const double b = np_ + ps[k];  // (old tree's edge adjacent to the new subtree).p + new p_sum
+                    dots[4] = fma(b, var[k] * np_, dots[4]);
+                    dots[5] = fma(b, vw, dots[5]);
+                }
+                warp_sum_n(dots);
+                if ((dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) || (dots[4] <= 0) ||
+                    (dots[5] <= 0)) {
+                    turned = true;
+                    break;
+                }
+            }
+        }
+        if (d_iter == maxd) hit_max = !tuning;  // for/else of nuts.py:220-221
+
+        // ---- the accepted position becomes the chain state -------------------------------------------
+        const double accept = exp(log_accept) / n_prop;  // nuts.py:479
+        const bool rec = P.store_warmup || !tuning;
+        const int t_out = P.store_warmup ? it : it - P.tune;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            const double qi = PQ[i];
+            q_s[i] = qi;
+            pq[k] = qi;
+            if (rec && i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = qi;
+        }
+        // ---- step_adapt.update (step_sizes.py:66-78); products/sums kept unfused like the Python scalars
+        if (adapting) {
+            const double w = 1.0 / (da_count + P.t0);
+            hbar = __dadd_rn(__dmul_rn(1.0 - w, hbar), __dmul_rn(w, P.target - accept));
+            log_step = da_mu - __dmul_rn(hbar, sqrt((double)da_count)) / P.gamma;
+            const double mk = pow((double)da_count, -P.kappa);
+            log_bar = __dadd_rn(__dmul_rn(mk, log_step), __dmul_rn(1.0 - mk, log_bar));
+            ++da_count;
+        }
+        // ---- potential.update (quadpotential.py:335-355, _WeightedVariance.add_sample :431-437) --------
+        if (tuning && P.mass_kind == B200_MASS_DIAG_ADAPT) {
+            if (k_samples > P.discard) {
+                fg_n += 1.0;
+                bg_n += 1.0;
+                double* fm = gvec(fg_m); double* fv = gvec(fg_v);
+                double* bm = gvec(bg_m); double* bv = gvec(bg_v);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    const double x = pq[k];
+                    double mean = fm[i];
+                    double d0 = x - mean;
+                    mean = __dadd_rn(mean, d0 / fg_n);
+                    fm[i] = mean;
+                    fv[i] = __dadd_rn(fv[i], __dmul_rn(d0, x - mean));
+                    mean = bm[i];
+                    d0 = x - mean;
+                    mean = __dadd_rn(mean, d0 / bg_n);
+                    bm[i] = mean;
+                    bv[i] = __dadd_rn(bv[i], __dmul_rn(d0, x - mean));
+                }
+            }
+            if (k_samples > window) {
+                const double* fv = gvec(fg_v);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i < n) var[k] = fmin(fmax(fv[i] / fg_n, 1e-12), 1e12);
+                }
+            }
+            if (k_samples > 0 && k_samples % window == 0) {
+                const int tm = fg_m, tv = fg_v;
+                fg_m = bg_m; fg_v = bg_v; fg_n = bg_n;
+                bg_m = tm; bg_v = tv; bg_n = 0.0;
+                double* bm = gvec(bg_m); double* bv = gvec(bg_v);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    bm[lane + 32 * k] = 0.0;
+                    bv[lane + 32 * k] = 0.0;
+                }
+            }
+            ++k_samples;
+        }
+        // ---- stats (nuts.py:478-489, base_hmc.py:275-286) --------------------------------------------
+        if (rec && lane == 0) {
+            const long long o = (long long)chain * T_out + t_out;
+            if (P.st.depth) P.st.depth[o] = depth;
+            if (P.st.tree_size) P.st.tree_size[o] = n_prop;
+            if (P.st.index_in_trajectory) P.st.index_in_trajectory[o] = m_pidx;
+            if (P.st.diverging) P.st.diverging[o] = diverged ? 1 : 0;
+            if (P.st.reached_max_treedepth) P.st.reached_max_treedepth[o] = hit_max ? 1 : 0;
+            if (P.st.step_size) P.st.step_size[o] = exp(log_step);
+            if (P.st.step_size_bar) P.st.step_size_bar[o] = exp(log_bar);
+            if (P.st.mean_tree_accept) P.st.mean_tree_accept[o] = accept;
+            if (P.st.energy) P.st.energy[o] = m_pe;
+            if (P.st.energy_error) P.st.energy_error[o] = m_pe - E0;
+            if (P.st.max_energy_error) P.st.max_energy_error[o] = max_de;
+            if (P.st.model_logp) P.st.model_logp[o] = m_plogp;
+        }
+        (void)turned;
+        __syncwarp();
+    }
+
+    // ---- end of run: hand the streams and adaptation results back --------------------------------------
+    if (lane == 0) {
+        b200_pcg64 r;
+        r.state_hi = (uint64_t)(rng.state >> 64); r.state_lo = (uint64_t)rng.state;
+        r.inc_hi = (uint64_t)(rng.inc >> 64); r.inc_lo = (uint64_t)rng.inc;
+        P.rng[chain] = r;
+        if (P.sm.grad_evals) P.sm.grad_evals[chain] = n_grad;
+        if (P.sm.bad_energy_at) P.sm.bad_energy_at[chain] = bad_at;
+        if (P.sm.final_step_size) P.sm.final_step_size[chain] = exp(log_bar);
+    }
+    if (P.sm.final_var) {
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < n) P.sm.final_var[(long long)chain * n + i] = var[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Batched logp + gradient: one warp per point.  Replaces ValueGradFunction._pytensor_function
+// (model/core.py:232-267) evaluated at C points.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, int NPL>
+__global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Model::Params M, int n, int C,
+                                                             const double* __restrict__ q,
+                                                             double* __restrict__ logp_out,
+                                                             double* __restrict__ grad_out) {
+    constexpr int NP = 32 * NPL;
+    extern __shared__ __align__(16) char smem_raw[];
+    __shared__ __align__(8) uint64_t tma_bar;
+    const size_t data_bytes = (Model::shared_bytes(M) + 15) & ~(size_t)15;
+    if (data_bytes) {
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        Model::stage(M, smem_raw, &tma_bar);
+        mbar_wait(&tma_bar, 0);
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * 2 * NP;
+    double* g_s = q_s + NP;
+    for (int c = blockIdx.x * wpb + wib; c < C; c += gridDim.x * wpb) {
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            q_s[i] = (i < n) ? q[(long long)c * n + i] : 0.0;
+            g_s[i] = 0.0;
+        }
+        __syncwarp();
+        const double lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < n) grad_out[(long long)c * n + i] = g_s[i];
+        }
+        if (lane == 0) logp_out[c] = lp;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Batched leapfrog with a diagonal potential: compute_state (n_steps == 0) or n_steps x _step
+// (integration.py:68-75, :109-145).  One warp per chain; State is struct-of-arrays in global memory.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, int NPL>
+__global__ void __launch_bounds__(256)
+    leapfrog_warp_kernel(const typename Model::Params M, int n, int C, const double* __restrict__ var_in,
+                         const double* __restrict__ eps_in, int n_steps, double* q, double* p_io, double* v_io,
+                         double* grad, double* energy, double* logp_io, long long* idx) {
+    constexpr int NP = 32 * NPL;
+    extern __shared__ __align__(16) char smem_raw[];
+    __shared__ __align__(8) uint64_t tma_bar;
+    const size_t data_bytes = (Model::shared_bytes(M) + 15) & ~(size_t)15;
+    if (data_bytes) {
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        Model::stage(M, smem_raw, &tma_bar);
+        mbar_wait(&tma_bar, 0);
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * 2 * NP;
+    double* g_s = q_s + NP;
+    for (int c = blockIdx.x * wpb + wib; c < C; c += gridDim.x * wpb) {
+        double var[NPL], p[NPL];
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            const bool in = i < n;
+            q_s[i] = in ? q[(long long)c * n + i] : 0.0;
+            g_s[i] = (in && n_steps > 0) ? grad[(long long)c * n + i] : 0.0;
+            p[k] = in ? p_io[(long long)c * n + i] : 0.0;
+            var[k] = in ? var_in[(long long)c * n + i] : 1.0;
+        }
+        __syncwarp();
+        double lp = 0.0, E = 0.0;
+        if (n_steps == 0) {
+            lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
+            __syncwarp();
+            double kk = 0.0;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) kk = fma(p[k], var[k] * p[k], kk);
+            E = 0.5 * warp_sum(kk) - lp;
+        } else {
+            const double es = eps_in[c], dt = 0.5 * es;
+            for (int s = 0; s < n_steps; ++s) {
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int i = lane + 32 * k;
+                    p[k] = fma(dt, g_s[i], p[k]);
+                    q_s[i] = fma(es, var[k] * p[k], q_s[i]);
+                }
+                __syncwarp();
+                lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
+                __syncwarp();
+                double kk = 0.0;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    p[k] = fma(dt, g_s[lane + 32 * k], p[k]);
+                    kk = fma(p[k], var[k] * p[k], kk);
+                }
+                E = 0.5 * warp_sum(kk) - lp;
+            }
+            if (lane == 0) idx[c] += (es > 0 ? 1 : (es < 0 ? -1 : 0)) * (long long)n_steps;
+        }
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < n) {
+                const long long o = (long long)c * n + i;
+                q[o] = q_s[i];
+                grad[o] = g_s[i];
+                p_io[o] = p[k];
+                v_io[o] = var[k] * p[k];
+            }
+        }
+        if (lane == 0) {
+            energy[c] = E;
+            logp_io[c] = lp;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace b200

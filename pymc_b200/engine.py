@@ -1,0 +1,200 @@
+"""Python face of the C-ABI engine: compiled model handle + the three hot-path entry points.
+
+``CompiledModel`` is the object the reference gets from ``Model.logp_dlogp_function(ravel_inputs=True)``
+(pymc/model/core.py:464-529): a handle whose call evaluates ``q -> (logp, dlogp)``, here batched over
+many points and backed by the model's hand-written CUDA function instead of a PyTensor C thunk.
+PyTorch is used only for device allocations when the caller wants results to stay in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error  # noqa: F401  (re-export)
+from .models import ModelSpec
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class CompiledModel:
+    """Observed data resident in HBM + dispatch to the model's fused logp/grad device function."""
+
+    def __init__(self, spec: ModelSpec, device: int | None = None):
+        self.spec = spec
+        self.n = spec.n
+        self._lib = _lib.load()
+        _lib.require_gpu()
+        if device is not None:
+            _lib.check(self._lib.b200_set_device(device))
+        d = _lib.ModelDesc()
+        d.kind, d.n = spec.kind, spec.n
+        keep = []
+
+        def hold(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+
+        data = spec.data
+        if spec.name == "eight_schools":
+            d.n_obs = len(data["y"])
+            d.y, d.aux = hold(data["y"], np.float64), hold(data["sigma"], np.float64)
+        elif spec.name == "radon":
+            d.n_obs, d.n_groups = len(data["y"]), spec.meta["n_counties"]
+            d.x, d.y = hold(data["floor"], np.float64), hold(data["y"], np.float64)
+            d.idx = hold(data["county_idx"], np.int32)
+        elif spec.name == "logistic":
+            d.n_obs = data["X"].shape[0]
+            d.x, d.y_u8 = hold(data["X"], np.float64), hold(data["y"], np.uint8)
+        elif spec.name == "stochvol":
+            d.n_obs = len(data["y"])
+            d.y = hold(data["y"], np.float64)
+        elif spec.name == "mvgauss":
+            d.x, d.aux = hold(data["prec"], np.float64), hold(data["cov"], np.float64)
+            d.scalar0 = spec.meta["logdet_L"]
+        handle = C.c_void_p()
+        _lib.check(self._lib.b200_model_create(C.byref(d), C.byref(handle)))
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.b200_model_destroy(h)
+
+    # ------------------------------------------------------------------------------------------
+    # a1: batched ValueGradFunction._pytensor_function
+    # ------------------------------------------------------------------------------------------
+    def logp_dlogp(self, q):
+        """q[C, n] (or [n]) -> (logp[C], grad[C, n]); NumPy in, NumPy out."""
+        q = _f64(q)
+        single = q.ndim == 1
+        q2 = q.reshape(-1, self.n)
+        Cn = q2.shape[0]
+        logp = np.empty(Cn)
+        grad = np.empty((Cn, self.n))
+        _lib.check(self._lib.b200_logp_dlogp(self._h, q2.ctypes.data, Cn, logp.ctypes.data, grad.ctypes.data, _lib.MEM_HOST, None))
+        return (float(logp[0]), grad[0]) if single else (logp, grad)
+
+    # ------------------------------------------------------------------------------------------
+    # a2/a3: CpuLeapfrogIntegrator.compute_state / .step, batched, diagonal potential
+    # ------------------------------------------------------------------------------------------
+    def leapfrog(self, q, p, var, eps, n_steps, *, grad=None, idx=None):
+        """Advance C states by ``n_steps`` leapfrogs of signed size ``eps[C]`` (n_steps=0: start state only).
+
+        Returns dict(q, p, v, grad, energy, logp, idx) -- the fields of integration.State."""
+        q, p, var = (np.array(_f64(x).reshape(-1, self.n)) for x in (q, p, var))
+        Cn = q.shape[0]
+        eps = np.broadcast_to(_f64(eps), (Cn,)).copy()
+        if n_steps > 0 and grad is None:
+            start = self.leapfrog(q, p, var, eps, 0)
+            grad = start["grad"]
+        g = np.zeros((Cn, self.n)) if grad is None else np.array(_f64(grad).reshape(Cn, self.n))
+        v = np.empty((Cn, self.n))
+        energy, logp = np.empty(Cn), np.empty(Cn)
+        ix = np.zeros(Cn, dtype=np.int64) if idx is None else np.array(idx, dtype=np.int64).reshape(Cn)
+        _lib.check(
+            self._lib.b200_leapfrog(
+                self._h, var.ctypes.data, eps.ctypes.data, int(n_steps), Cn, q.ctypes.data, p.ctypes.data,
+                v.ctypes.data, g.ctypes.data, energy.ctypes.data, logp.ctypes.data, ix.ctypes.data, _lib.MEM_HOST, None,
+            )
+        )
+        return dict(q=q, p=p, v=v, grad=g, energy=energy, logp=logp, idx=ix)
+
+    # ------------------------------------------------------------------------------------------
+    # a12+a13+a16: the whole multi-chain NUTS run
+    # ------------------------------------------------------------------------------------------
+    def nuts_run(self, q0, rng_states, *, tune, draws, var0=None, mean0=None, z=None, store_warmup=True,
+                 mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
+                 k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
+                 mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
+                 device_outputs=False, stats=True):
+        """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
+
+        ``rng_states``: structured array (``_lib.PCG64_DTYPE``) of the chains' NumPy PCG64 step streams
+        (see ``pymc_b200.rng``); updated in place.  ``z``: optional momentum noise [C, tune+draws, n]
+        (NumPy ``Generator.normal`` for draw-parity with the reference); otherwise generated on device.
+        ``device_outputs=True`` keeps draws/stats as torch CUDA tensors (no D2H copy)."""
+        q0 = _f64(q0).reshape(-1, self.n)
+        Cn = q0.shape[0]
+        Ttot = tune + draws
+        T = Ttot if store_warmup else draws
+        cfg = _lib.NutsCfg()
+        cfg.chains, cfg.tune, cfg.draws = Cn, int(tune), int(draws)
+        cfg.max_treedepth, cfg.early_max_treedepth = int(max_treedepth), int(early_max_treedepth)
+        cfg.adapt_step_size = int(bool(adapt_step_size))
+        cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT}[mass]
+        cfg.momentum_source = _lib.MOMENTUM_DEVICE_PHILOX if z is None else _lib.MOMENTUM_HOST_BUFFER
+        cfg.store_warmup = int(bool(store_warmup))
+        cfg.step_scale, cfg.target_accept, cfg.gamma, cfg.k, cfg.t0, cfg.Emax = (
+            float(step_scale), float(target_accept), float(gamma), float(k), float(t0), float(Emax))
+        cfg.mass_initial_weight = float(mass_initial_weight)
+        cfg.adaptation_window, cfg.discard_window = int(adaptation_window), int(discard_window)
+        cfg.philox_seed = int(philox_seed) & 0xFFFFFFFFFFFFFFFF
+        if rng_states.dtype != _lib.PCG64_DTYPE or rng_states.shape != (Cn,):
+            raise ValueError("rng_states must be a (chains,) array of _lib.PCG64_DTYPE")
+
+        if device_outputs:
+            import torch
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            mem = _lib.MEM_DEVICE
+            to_dev = lambda a: None if a is None else torch.as_tensor(_f64(a), device=dev)  # noqa: E731
+            q0_b, var0_b, mean0_b, z_b = to_dev(q0), to_dev(var0), to_dev(mean0), to_dev(z)
+            rng_b = torch.as_tensor(rng_states.view(np.uint64).reshape(Cn, 4).view(np.int64), device=dev)
+            draws_b = torch.full((Cn, T, self.n), float("nan"), dtype=torch.float64, device=dev)
+            tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
+            mk = lambda shape, dt: torch.zeros(shape, dtype=tdt[dt], device=dev)  # noqa: E731
+        else:
+            mem = _lib.MEM_HOST
+            q0_b = q0
+            var0_b = None if var0 is None else _f64(var0).reshape(Cn, self.n)
+            mean0_b = None if mean0 is None else _f64(mean0).reshape(Cn, self.n)
+            z_b = None if z is None else _f64(z).reshape(Cn, Ttot, self.n)
+            rng_b = rng_states
+            draws_b = np.empty((Cn, T, self.n))
+            mk = lambda shape, dt: np.zeros(shape, dtype=dt)  # noqa: E731
+
+        st, st_arr = _lib.Stats(), {}
+        if stats:
+            for name, dt in _lib.STAT_FIELDS:
+                st_arr[name] = mk((Cn, T), dt)
+                setattr(st, name, _lib.ptr(st_arr[name]))
+        sm, sm_arr = _lib.ChainSummary(), {}
+        for name, dt in _lib.SUMMARY_FIELDS:
+            sm_arr[name] = mk((Cn, self.n) if name == "final_var" else (Cn,), dt)
+            setattr(sm, name, _lib.ptr(sm_arr[name]))
+
+        _lib.check(
+            self._lib.b200_nuts_run(
+                self._h, C.byref(cfg), _lib.ptr(q0_b), _lib.ptr(var0_b), _lib.ptr(mean0_b), _lib.ptr(rng_b),
+                _lib.ptr(z_b), _lib.ptr(draws_b), C.byref(st), C.byref(sm), mem, None,
+            )
+        )
+        if device_outputs:
+            rng_states[:] = rng_b.cpu().numpy().view(np.uint64).reshape(Cn, 4).view(_lib.PCG64_DTYPE).reshape(Cn)
+        ms, launches = _lib.last_kernel_ms()
+        return NutsResult(draws=draws_b, stats=st_arr, summary=sm_arr, kernel_ms=ms, launches=launches,
+                          tune=tune, n_draws=draws, store_warmup=store_warmup)
+
+
+@dataclass
+class NutsResult:
+    draws: object  # [C, T, n] unconstrained positions (NumPy or torch CUDA)
+    stats: dict
+    summary: dict
+    kernel_ms: float
+    launches: int
+    tune: int
+    n_draws: int
+    store_warmup: bool
+
+    @property
+    def grad_evals(self) -> int:
+        """Leapfrog gradient evaluations (sum of tree_size, the reference's own stat, hmc/nuts.py:485)."""
+        ts = self.stats["tree_size"]
+        return int(ts.sum())

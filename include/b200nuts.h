@@ -175,6 +175,8 @@ int b200_leapfrog(b200_model* model, const double* var, const double* eps, int32
  *   var0[C][n]        initial diagonal inverse mass (ones for jitter+adapt_diag); NULL = ones
  *   mean0[C][n]       DIAG_ADAPT: initial mean of the foreground estimator (init_nuts passes the mean
  *                     start point over chains, mcmc.py:1890); NULL = zeros
+ *   eps0[C]           optional per-chain initial step size overriding step_scale / n**0.25 (a chain resumed
+ *                     from a saved sampling_state carries its own step size, base_hmc.py:61-71); NULL = default
  *   rng[C]            per-chain NumPy PCG64 `step` stream states; updated in place on return
  *   z[C][Ttot][n]     momentum noise when momentum_source == B200_MOMENTUM_HOST_BUFFER, else NULL
  *   draws_out[C][T][n]  accepted positions (unconstrained), T per `store_warmup`
@@ -182,7 +184,7 @@ int b200_leapfrog(b200_model* model, const double* var, const double* eps, int32
  *   mem               memory space of ALL the buffers above
  */
 int b200_nuts_run(b200_model* model, const b200_nuts_cfg* cfg, const double* q0, const double* var0,
-                  const double* mean0, b200_pcg64* rng, const double* z, double* draws_out,
+                  const double* mean0, const double* eps0, b200_pcg64* rng, const double* z, double* draws_out,
                   const b200_stats* stats, const b200_chain_summary* summary, int32_t mem,
                   void* stream);
 

@@ -26,14 +26,14 @@ STAT_KEYS = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_
              "step_size_bar", "mean_tree_accept", "energy", "energy_error", "max_energy_error", "model_logp"]
 
 
-def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None):
+def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None, init_var=None):
     """One chain through the verbatim reference.  adapt=True: DiagAdapt(mean=q0, ones, weight 10) + dual
     averaging (what init_nuts builds, mcmc.py:1890-1894); adapt=False: fixed QuadPotentialDiag(var), fixed eps."""
     f = logp_numpy.make_logp(spec)
     qp = ref_loader.quadpotential()
     n = spec.n
     if adapt:
-        pot = qp.QuadPotentialDiagAdapt(n, q0.copy(), np.ones(n), 10)
+        pot = qp.QuadPotentialDiagAdapt(n, q0.copy(), np.ones(n) if init_var is None else np.array(init_var, dtype="d"), 10)
     else:
         pot = qp.QuadPotentialDiag(np.ones(n) if var is None else np.asarray(var, dtype="d"))
     start = {v.name: q0[v.offset : v.offset + v.size].copy() for v in spec.vars}
@@ -45,15 +45,22 @@ def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nut
     if tune == 0:
         step.tune = False
     pt, qs, sts = start, [], []
+    pre_rng, pre_var, used_eps = [], [], []
     for i in range(tune + draws):
         if i == tune:
             step.stop_tuning()
+        # what a single-draw replay ("teacher forcing") needs: stream position, mass matrix, step size
+        s = step.rng.bit_generator.state["state"]
+        pre_rng.append([s["state"] >> 64, s["state"] & (2**64 - 1), s["inc"] >> 64, s["inc"] & (2**64 - 1)])
+        pre_var.append(np.array(step.potential._var if adapt else step.potential.v))
         pt, st = step.step(pt)
+        used_eps.append(float(step.step_size))  # set inside astep: the eps this draw integrated with
         qs.append(np.concatenate([np.ravel(pt[v.name]) for v in spec.vars]))
         sts.append(st[0])
     stats = {k: np.array([s[k] for s in sts]) for k in STAT_KEYS}
     final_var = np.array(step.potential._var if adapt else step.potential.v)
-    return np.array(qs), stats, final_var, float(step.step_size)
+    extra = dict(pre_rng=np.array(pre_rng, dtype=np.uint64), pre_var=np.array(pre_var), used_eps=np.array(used_eps))
+    return np.array(qs), stats, final_var, float(step.step_size), extra
 
 
 def noise(seed, T, n):
@@ -63,21 +70,27 @@ def noise(seed, T, n):
     return np.array([g.normal(size=n) for _ in range(T)])
 
 
-def case(name, spec_name, spec_args, q0s, seeds, *, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None):
+def case(name, spec_name, spec_args, q0s, seeds, *, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None,
+         init_var=None):
     spec = models.BUILDERS[spec_name](**spec_args)
     C = len(seeds)
-    Q, ST, FV, FE, Z = [], [], [], [], []
+    Q, ST, FV, FE, Z, EX = [], [], [], [], [], []
     for c in range(C):
         v = None if var is None else var[c]
         e = None if eps is None else float(eps[c])
-        q, st, fv, fe = run_reference(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, adapt=adapt, var=v,
-                                      eps=e, nuts_kwargs=nuts_kwargs)
-        Q.append(q); ST.append(st); FV.append(fv); FE.append(fe)
+        q, st, fv, fe, ex = run_reference(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, adapt=adapt, var=v,
+                                          eps=e, nuts_kwargs=nuts_kwargs,
+                                          init_var=None if init_var is None else init_var[c])
+        Q.append(q); ST.append(st); FV.append(fv); FE.append(fe); EX.append(ex)
         Z.append(noise(seeds[c], tune + draws, spec.n))
     out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, adapt=adapt, draws_q=np.array(Q),
                z=np.array(Z), final_var=np.array(FV), final_step_size=np.array(FE),
                var=np.array(var) if var is not None else np.ones((C, spec.n)),
-               eps=np.array(eps) if eps is not None else np.full(C, np.nan))
+               eps=np.array(eps) if eps is not None else np.full(C, np.nan),
+               init_var=np.array(init_var) if init_var is not None else np.ones((C, spec.n)),
+               step_scale=(nuts_kwargs or {}).get("step_scale", 0.25))
+    for k in EX[0]:
+        out[k] = np.array([e[k] for e in EX])
     for k in STAT_KEYS:
         out["stat_" + k] = np.array([s[k] for s in ST])
     os.makedirs(OUT, exist_ok=True)
@@ -96,17 +109,25 @@ def main():
     case("eight_schools_fixed", "eight_schools", {}, [np.zeros(10)], [20240922], tune=0, draws=40, adapt=False)
     rng = np.random.default_rng(11)
     q0s = [es.initial_point() + rng.uniform(-1, 1, 10) for _ in range(3)]
-    case("eight_schools_adapt", "eight_schools", {}, q0s, [101, 102, 103], tune=300, draws=100, adapt=True)
+    e = case("eight_schools_adapt", "eight_schools", {}, q0s, [101, 102, 103], tune=300, draws=100, adapt=True)
+    case("eight_schools_warm_adapt", "eight_schools", {}, [e["draws_q"][0, -1]], [601], tune=250, draws=30, adapt=True,
+         init_var=e["final_var"][:1], nuts_kwargs={"step_scale": float(e["final_step_size"][0]) / 10 * 10**0.25})
     # --- std normal n=100, fixed eps ---
     q0s = [rng.standard_normal(100) for _ in range(2)]
     case("std_normal_fixed", "std_normal", {"n": 100}, q0s, [7, 8], tune=0, draws=30, adapt=False)
     # --- Radon: full adaptation from jittered starts, then a fixed-eps/fixed-mass replay from the warm state ---
     rd = models.radon()
     q0s = [rd.initial_point() + rng.uniform(-1, 1, rd.n) for _ in range(2)]
-    a = case("radon_adapt", "radon", {}, q0s, [201, 202], tune=400, draws=50, adapt=True)
-    warm_q = [a["draws_q"][c, -1] for c in range(2)]
-    case("radon_fixed", "radon", {}, warm_q, [301, 302], tune=0, draws=40, adapt=False, var=a["final_var"],
-         eps=a["final_step_size"])
+    a = case("radon_adapt", "radon", {}, q0s[:1], [201], tune=400, draws=50, adapt=True)
+    b = run_reference(rd, q0s[1], seed=202, tune=400, draws=1, adapt=True)
+    warm_q = [a["draws_q"][0, -1], b[0][-1]]
+    warm_var = np.array([a["final_var"][0], b[2]])
+    warm_eps = np.array([a["final_step_size"][0], b[3]])
+    case("radon_fixed", "radon", {}, warm_q, [301, 302], tune=0, draws=40, adapt=False, var=warm_var, eps=warm_eps)
+    # adaptation ON from a warm state (tuned mass matrix as initial_diag, eps0 = tuned/10 so mu = log(tuned)):
+    # exercises dual averaging and both Welford window switches in the non-chaotic regime
+    case("radon_warm_adapt", "radon", {}, warm_q[:1], [501], tune=250, draws=30, adapt=True, init_var=warm_var[:1],
+         nuts_kwargs={"step_scale": float(warm_eps[0]) / 10 * rd.n**0.25})
     # small ragged radon (counties with 1..n obs, fewer counties than lanes), early treedepth cap exercised
     q0s = [np.zeros(2 * 7 + 5) + rng.uniform(-1, 1, 19)]
     case("radon_small_adapt", "radon", {"n_obs": 40, "n_counties": 7, "seed": 5}, q0s, [401], tune=250, draws=50,

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200nuts.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "libb200nuts.so"))  # override: A/B builds while tuning
 
 MEM_HOST, MEM_DEVICE = 0, 1
 MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE = 0, 1, 2
@@ -119,7 +119,7 @@ SYMBOLS = [
     (
         "b200_nuts_run",
         C.c_int,
-        [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 6 + [C.POINTER(Stats), C.POINTER(ChainSummary), C.c_int32, C.c_void_p],
+        [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 7 + [C.POINTER(Stats), C.POINTER(ChainSummary), C.c_int32, C.c_void_p],
     ),
     ("b200_last_kernel_ms", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     ("b200_measure_fp64_tflops", C.c_int, [C.POINTER(C.c_double)]),

@@ -97,38 +97,34 @@ static int prepare_radon(b200_model* m, const b200_model_desc* d) {
         if (c < 0 || c >= J) return fail("radon: county_idx[%lld]=%d out of range", i, c);
         members[c].push_back((int)i);
     }
-    // longest-processing-time assignment of counties to the 32 lanes
-    std::vector<int> order(J);
-    std::iota(order.begin(), order.end(), 0);
+    // counties sorted by size; row j = counties order[32j .. 32j+31], one per lane, padded to the row's longest
+    std::vector<int> order;
+    std::vector<int> empty;
+    for (int c = 0; c < J; ++c) (members[c].empty() ? empty : order).push_back(c);
     std::stable_sort(order.begin(), order.end(),
                      [&](int a, int b) { return members[a].size() > members[b].size(); });
-    std::vector<std::vector<int>> lane_c(32);
-    std::vector<long long> load(32, 0);
-    std::vector<int> empty;
-    for (int c : order) {
-        if (members[c].empty()) { empty.push_back(c); continue; }
-        int best = 0;
-        for (int l = 1; l < 32; ++l)
-            if (load[l] < load[best]) best = l;
-        lane_c[best].push_back(c);
-        load[best] += (long long)members[c].size();
+    const int M = std::max<int>(1, ((int)order.size() + 31) / 32);
+    std::vector<int32_t> seg((size_t)M * 32 + ((M + 3) & ~3), 0);
+    for (size_t i = 0; i < (size_t)M * 32; ++i) seg[i] = 0xffff;  // idle lane
+    int K = 0;
+    std::vector<int> row_off(M, 0), row_len(M, 0);
+    for (int j = 0; j < M; ++j) {
+        row_off[j] = K;
+        for (int l = 0; l < 32 && (size_t)(j * 32 + l) < order.size(); ++l)
+            row_len[j] = std::max<int>(row_len[j], (int)members[order[j * 32 + l]].size());
+        K += row_len[j];
     }
-    int K = 0, M = 1;
-    for (int l = 0; l < 32; ++l) {
-        K = std::max<int>(K, (int)load[l]);
-        M = std::max<int>(M, (int)lane_c[l].size());
-    }
-    if (K >= 0x7fff) return fail("radon: more than 32766 observations per lane unsupported");
+    if (K >= 0xffff) return fail("radon: padded observation rows exceed 65534");
+    K = std::max(K, 1);
     std::vector<double2> xy((size_t)K * 32, make_double2(0.0, 0.0));
-    std::vector<int32_t> seg((size_t)(M + 1) * 32, 0);
-    for (int l = 0; l < 32; ++l) {
-        int k = 0;
-        for (size_t j = 0; j < lane_c[l].size(); ++j) {
-            const int c = lane_c[l][j];
+    for (int j = 0; j < M; ++j) {
+        for (int l = 0; l < 32 && (size_t)(j * 32 + l) < order.size(); ++l) {
+            const int c = order[j * 32 + l];
+            int k = row_off[j];
             for (int i : members[c]) xy[(size_t)(k++) * 32 + l] = make_double2(d->x[i], d->y[i]);
-            seg[j * 32 + l] = (k << 16) | c;
+            seg[(size_t)j * 32 + l] = ((int32_t)members[c].size() << 16) | c;
         }
-        seg[(size_t)M * 32 + l] = k;  // observations walked by the lane
+        seg[(size_t)M * 32 + j] = (row_off[j] << 16) | row_len[j];
     }
     RadonModel::Params& P = m->radon;
     P.K = K; P.M = M; P.J = J; P.n_obs = (int)N; P.E = (int)empty.size();
@@ -366,7 +362,7 @@ struct NutsLaunch {
         constexpr int NP = 32 * NPL;
         int wpb = env_int("B200_NUTS_WPB", 4);
         int hot = env_int("B200_NUTS_HOT", 2);
-        wpb = std::max(1, std::min(wpb, 8));
+        wpb = std::max(1, std::min(wpb, B200_NUTS_THREADS / 32));
         hot = std::max(0, std::min(hot, P.max_td));
         const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
         size_t smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot);
@@ -394,7 +390,8 @@ struct NutsLaunch {
 };
 
 extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const double* q0, const double* var0,
-                             const double* mean0, b200_pcg64* rng, const double* z, double* draws_out,
+                             const double* mean0, const double* eps0, b200_pcg64* rng, const double* z,
+                             double* draws_out,
                              const b200_stats* stats, const b200_chain_summary* summary, int32_t mem,
                              void* stream) {
     if (!m || !cfg || !q0 || !rng || !draws_out) return fail("b200_nuts_run: null argument");
@@ -416,9 +413,10 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     const long long Ttot = (long long)cfg->tune + cfg->draws;
     const long long T = cfg->store_warmup ? Ttot : cfg->draws;
     const size_t vb = (size_t)C * n * sizeof(double);
-    Staged s_q0, s_var0, s_mean0, s_rng, s_z, s_draws;
+    Staged s_q0, s_var0, s_mean0, s_eps0, s_rng, s_z, s_draws;
     if (stage_in(s_q0, q0, vb, mem, true, false, st) || stage_in(s_var0, var0, vb, mem, true, false, st) ||
         stage_in(s_mean0, mean0, vb, mem, true, false, st) ||
+        stage_in(s_eps0, eps0, (size_t)C * sizeof(double), mem, true, false, st) ||
         stage_in(s_rng, rng, (size_t)C * sizeof(b200_pcg64), mem, true, true, st) ||
         stage_in(s_z, cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER ? z : nullptr, vb * Ttot, mem, true, false, st) ||
         stage_in(s_draws, draws_out, vb * T, mem, false, true, st))
@@ -472,7 +470,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     P.Emax = cfg->Emax; P.init_weight = cfg->mass_initial_weight;
     P.philox_seed = cfg->philox_seed;
     P.q0 = (const double*)s_q0.ptr(); P.var0 = (const double*)s_var0.ptr();
-    P.mean0 = (const double*)s_mean0.ptr(); P.z = (const double*)s_z.ptr();
+    P.mean0 = (const double*)s_mean0.ptr(); P.eps0c = (const double*)s_eps0.ptr(); P.z = (const double*)s_z.ptr();
     P.rng = (b200_pcg64*)s_rng.ptr(); P.draws_out = (double*)s_draws.ptr();
     P.st = ds; P.sm = dsum;
 

@@ -86,25 +86,29 @@ struct EightSchoolsModel {
 //   alpha_c = mu_a + sigma_a a_c ; beta_c = mu_b + sigma_b b_c ; y_i ~ Normal(alpha_c(i) + beta_c(i) x_i, eps)
 //   mu_* ~ Normal(0, 100**2) ; sigma_*, eps ~ HalfCauchy(5) ; a, b ~ Normal(0,1)
 // Gradient: SURVEY Appendix C-2.  The per-county segmented sums G_alpha, G_beta are the per-chain
-// reduction: observations are grouped by county at model-create time and counties are dealt to
-// the 32 lanes by longest-processing-time so every lane walks ~n_obs/32 observations; a lane keeps
-// its county's (alpha, beta, G_alpha, G_beta) in registers and finishes that county's two gradient
-// entries itself when the county ends.  The (x, y) pairs are an ELL array [K][32] of double2 staged
-// once per CTA into shared memory by bulk TMA and shared by all the CTA's chains.
+// reduction.  At model-create time counties are sorted by size and dealt to the 32 lanes row by row
+// (row j = the j-th county of every lane; sorting makes the sizes within a row nearly equal), and each
+// row is padded to its longest county, so all lanes reach the end of their county at the SAME inner
+// iteration: the loop body is branch-free (padding is masked by a select) and the "county finished"
+// epilogue is warp-uniform.  A lane keeps its county's (alpha, beta, G_alpha, G_beta) in registers and
+// completes that county's two gradient entries itself.  The (x, y) pairs are an ELL array [K][32] of
+// double2 staged once per CTA into shared memory by bulk TMA and shared by all the CTA's chains.
 // ------------------------------------------------------------------------------------------------
 struct RadonModel {
     struct Params {
-        const double2* xy;   // [K][32]  (floor_i, y_i) in lane-major ELL order
-        const int32_t* seg;  // [M][32]  (end_k << 16) | county   (end_k = one past the county's last k)
-                             // row M of seg: observations walked by each lane
+        const double2* xy;   // [K][32]  (floor_i, y_i); row j occupies k in [off_j, off_j + len_j)
+        const int32_t* seg;  // [M][32]  (count << 16) | county, county = 0xffff: lane idle in this row
+                             // followed by rows[M]: (off_j << 16) | len_j   (padded to a multiple of 4 ints)
         const int32_t* empty;  // [E] counties without observations (prior terms only)
         int K, M, J, n_obs, E;
     };
     __host__ __device__ static size_t xy_bytes(const Params& P) { return (size_t)P.K * 32 * sizeof(double2); }
-    __host__ __device__ static size_t seg_bytes(const Params& P) { return (size_t)(P.M + 1) * 32 * sizeof(int32_t); }
+    __host__ __device__ static size_t seg_bytes(const Params& P) {
+        return ((size_t)P.M * 32 + ((P.M + 3) & ~3)) * sizeof(int32_t);
+    }
     __host__ __device__ static size_t shared_bytes(const Params& P) { return xy_bytes(P) + seg_bytes(P); }
 
-    // CTA-wide: thread 0 issues two bulk-TMA copies (xy, then seg+tot which are contiguous in HBM).
+    // CTA-wide: thread 0 issues two bulk-TMA copies (xy, then seg+rows which are contiguous in HBM).
     __device__ static void stage(const Params& P, char* smem, uint64_t* bar) {
         if (threadIdx.x == 0) {
             const uint32_t b0 = (uint32_t)xy_bytes(P), b1 = (uint32_t)seg_bytes(P);
@@ -116,8 +120,9 @@ struct RadonModel {
 
     template <int NPL>
     __device__ static double eval(const Params& P, const char* smem, const double* q_s, double* g_s, int lane) {
-        const double2* xy = reinterpret_cast<const double2*>(smem);
+        const double2* xy = reinterpret_cast<const double2*>(smem) + lane;
         const int32_t* seg = reinterpret_cast<const int32_t*>(smem + xy_bytes(P));
+        const int32_t* rows = seg + P.M * 32;
         const int J = P.J;
         const double mu_a = q_s[0], mu_b = q_s[2];
         // one exp() for the warp: lanes 0,1,2 take log sigma_a, log sigma_b, log eps
@@ -139,46 +144,36 @@ struct RadonModel {
 
         // acc: S2, sum Ga, sum a*Ga, sum Gb, sum b*Gb, sum a^2, sum b^2   (Ga/Gb raw: sums of residuals)
         double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        const int total = seg[P.M * 32 + lane];
-        int j = 0;
-        int sg = seg[lane];
-        int end = sg >> 16, c = sg & 0xffff;
-        double a_c = 0.0, b_c = 0.0, al = 0.0, be = 0.0, Ga = 0.0, Gb = 0.0;
-        if (total > 0) {
-            a_c = q_s[4 + c];
-            b_c = q_s[4 + J + c];
-            al = fma(sa, a_c, mu_a);
-            be = fma(sb, b_c, mu_b);
-        }
-        for (int k = 0; k < P.K; ++k) {
-            if (k < total) {
-                const double2 d = xy[k * 32 + lane];
-                const double r = d.y - fma(be, d.x, al);
-                acc[0] = fma(r, r, acc[0]);
+        for (int j = 0; j < P.M; ++j) {
+            const int rw = rows[j];
+            const int len = rw & 0xffff;
+            const double2* row = xy + (rw >> 16) * 32;
+            const int sg = seg[j * 32 + lane];
+            const int cnt = sg >> 16, c = sg & 0xffff;
+            const bool live = c != 0xffff;
+            const int ci = live ? c : 0;
+            const double a_c = q_s[4 + ci], b_c = q_s[4 + J + ci];
+            const double al = fma(sa, a_c, mu_a), be = fma(sb, b_c, mu_b);
+            double Ga = 0.0, Gb = 0.0, S2 = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) {
+                const double2 d = row[k * 32];
+                double r = d.y - fma(be, d.x, al);
+                r = (k < cnt) ? r : 0.0;  // padding contributes exact zeros
+                S2 = fma(r, r, S2);
                 Ga += r;
                 Gb = fma(r, d.x, Gb);
-                if (k + 1 == end) {  // county finished: its two gradient entries are complete
-                    g_s[4 + c] = fma(sa_ie2, Ga, -a_c);
-                    g_s[4 + J + c] = fma(sb_ie2, Gb, -b_c);
-                    acc[1] += Ga;
-                    acc[2] = fma(a_c, Ga, acc[2]);
-                    acc[3] += Gb;
-                    acc[4] = fma(b_c, Gb, acc[4]);
-                    acc[5] = fma(a_c, a_c, acc[5]);
-                    acc[6] = fma(b_c, b_c, acc[6]);
-                    ++j;
-                    if (k + 1 < total) {
-                        sg = seg[j * 32 + lane];
-                        end = sg >> 16;
-                        c = sg & 0xffff;
-                        a_c = q_s[4 + c];
-                        b_c = q_s[4 + J + c];
-                        al = fma(sa, a_c, mu_a);
-                        be = fma(sb, b_c, mu_b);
-                        Ga = 0.0;
-                        Gb = 0.0;
-                    }
-                }
+            }
+            acc[0] += S2;
+            if (live) {  // county finished: its two gradient entries are complete
+                g_s[4 + c] = fma(sa_ie2, Ga, -a_c);
+                g_s[4 + J + c] = fma(sb_ie2, Gb, -b_c);
+                acc[1] += Ga;
+                acc[2] = fma(a_c, Ga, acc[2]);
+                acc[3] += Gb;
+                acc[4] = fma(b_c, Gb, acc[4]);
+                acc[5] = fma(a_c, a_c, acc[5]);
+                acc[6] = fma(b_c, b_c, acc[6]);
             }
         }
         for (int e = lane; e < P.E; e += 32) {  // counties with no observations: prior terms only

@@ -39,6 +39,7 @@ struct NutsDev {
     const double* q0;     // [C][n]
     const double* var0;   // [C][n] or null
     const double* mean0;  // [C][n] or null
+    const double* eps0c;  // [C] or null: per-chain initial step size
     const double* z;      // [C][Ttot][n] or null
     b200_pcg64* rng;      // [C]
     double* draws_out;    // [C][T][n]
@@ -60,8 +61,14 @@ __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot) {
     return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double);
 }
 
+#ifndef B200_NUTS_THREADS
+#define B200_NUTS_THREADS 256  // CTA size cap of the NUTS kernel (warps per CTA <= THREADS/32)
+#endif
+#ifndef B200_NUTS_MINBLOCKS
+#define B200_NUTS_MINBLOCKS 1  // __launch_bounds__ min CTAs/SM: the register budget knob
+#endif
 template <class Model, int NPL>
-__global__ void __launch_bounds__(256) nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
+__global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
     constexpr int NP = 32 * NPL;
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
@@ -123,8 +130,9 @@ __global__ void __launch_bounds__(256) nuts_warp_kernel(const NutsDev P, const t
     int k_samples = 0, window = P.window;
 
     // dual averaging (step_sizes.py:50-57)
-    double log_step = log(P.eps0), log_bar = log_step, hbar = 0.0;
-    const double da_mu = log(10.0 * P.eps0);
+    const double eps_init = P.eps0c ? P.eps0c[chain] : P.eps0;
+    double log_step = log(eps_init), log_bar = log_step, hbar = 0.0;
+    const double da_mu = log(10.0 * eps_init);
     int da_count = 1;
 
     Pcg64 rng;

@@ -108,7 +108,7 @@ class CompiledModel:
     # ------------------------------------------------------------------------------------------
     # a12+a13+a16: the whole multi-chain NUTS run
     # ------------------------------------------------------------------------------------------
-    def nuts_run(self, q0, rng_states, *, tune, draws, var0=None, mean0=None, z=None, store_warmup=True,
+    def nuts_run(self, q0, rng_states, *, tune, draws, var0=None, mean0=None, eps0=None, z=None, store_warmup=True,
                  mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
                  k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
@@ -145,6 +145,7 @@ class CompiledModel:
             mem = _lib.MEM_DEVICE
             to_dev = lambda a: None if a is None else torch.as_tensor(_f64(a), device=dev)  # noqa: E731
             q0_b, var0_b, mean0_b, z_b = to_dev(q0), to_dev(var0), to_dev(mean0), to_dev(z)
+            eps0_b = to_dev(eps0)
             rng_b = torch.as_tensor(rng_states.view(np.uint64).reshape(Cn, 4).view(np.int64), device=dev)
             draws_b = torch.full((Cn, T, self.n), float("nan"), dtype=torch.float64, device=dev)
             tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
@@ -155,6 +156,7 @@ class CompiledModel:
             var0_b = None if var0 is None else _f64(var0).reshape(Cn, self.n)
             mean0_b = None if mean0 is None else _f64(mean0).reshape(Cn, self.n)
             z_b = None if z is None else _f64(z).reshape(Cn, Ttot, self.n)
+            eps0_b = None if eps0 is None else np.broadcast_to(_f64(eps0), (Cn,)).copy()
             rng_b = rng_states
             draws_b = np.empty((Cn, T, self.n))
             mk = lambda shape, dt: np.zeros(shape, dtype=dt)  # noqa: E731
@@ -171,7 +173,7 @@ class CompiledModel:
 
         _lib.check(
             self._lib.b200_nuts_run(
-                self._h, C.byref(cfg), _lib.ptr(q0_b), _lib.ptr(var0_b), _lib.ptr(mean0_b), _lib.ptr(rng_b),
+                self._h, C.byref(cfg), _lib.ptr(q0_b), _lib.ptr(var0_b), _lib.ptr(mean0_b), _lib.ptr(eps0_b), _lib.ptr(rng_b),
                 _lib.ptr(z_b), _lib.ptr(draws_b), C.byref(st), C.byref(sm), mem, None,
             )
         )

@@ -1,0 +1,93 @@
+"""Shared helpers: model specs per golden file, GPU replay (free-running and single-draw), oracle replay."""
+import numpy as np
+
+from pymc_b200 import _lib, models
+
+SPEC_OF = {
+    "std_normal_fixed": lambda: models.std_normal(100),
+    "eight_schools_fixed": models.eight_schools,
+    "eight_schools_adapt": models.eight_schools,
+    "eight_schools_warm_adapt": models.eight_schools,
+    "radon_fixed": models.radon,
+    "radon_adapt": models.radon,
+    "radon_warm_adapt": models.radon,
+    "radon_small_adapt": lambda: models.radon(40, 7, 5),
+}
+TREE_KW = {"radon_small_adapt": dict(max_treedepth=6, early_max_treedepth=4)}
+DISCRETE = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_max_treedepth"]
+CONTINUOUS = ["step_size", "step_size_bar", "mean_tree_accept", "energy", "energy_error", "max_energy_error", "model_logp"]
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    with np.errstate(invalid="ignore"):
+        e = np.abs(a - b) / np.maximum(1e-300, np.maximum(np.abs(a), np.abs(b)))
+    e = np.where((a == b) | (np.isnan(a) & np.isnan(b)), 0.0, e)
+    return float(np.max(e)) if e.size else 0.0
+
+
+def start_states(d):
+    """PCG64 stream states at the start of every golden chain (pre_rng of draw 0)."""
+    return stream_states(d["pre_rng"][:, 0])
+
+
+def stream_states(arr_u64x4):
+    a = np.array(arr_u64x4, dtype=np.uint64, copy=True).reshape(-1, 4)  # copy: the engine advances states in place
+    return a.view(_lib.PCG64_DTYPE).reshape(-1)
+
+
+def gpu_free_run(cm, d, name, draws=None):
+    """Replay a golden case through b200_nuts_run with the golden inputs (start, streams, momentum noise)."""
+    tune, T = int(d["tune"]), int(d["tune"]) + int(d["draws"])
+    if draws is not None:  # only the first `draws` iterations (all must be in one phase)
+        assert draws <= tune or tune == 0
+        T = draws
+    kw = dict(TREE_KW.get(name, {}))
+    if bool(d["adapt"]):
+        kw.update(mass="diag_adapt", mean0=d["q0"], var0=d["init_var"], adapt_step_size=True, step_scale=float(d["step_scale"]))
+        t, dr = (T, 0) if draws is not None else (tune, int(d["draws"]))
+    else:
+        kw.update(mass="diag", var0=d["var"], adapt_step_size=False)
+        if not np.isnan(d["eps"][0]):
+            kw["eps0"] = d["eps"]
+        t, dr = 0, T
+    states = start_states(d)
+    res = cm.nuts_run(d["q0"], states, tune=t, draws=dr, z=np.ascontiguousarray(d["z"][:, :T]), **kw)
+    return res, states
+
+
+def gpu_single_draws(cm, d, name, chain=0):
+    """Teacher forcing: every golden draw t replayed as an independent one-iteration chain started from the
+    golden state before it (position, stream position, mass matrix, step size)."""
+    T = int(d["tune"]) + int(d["draws"])
+    q_prev = np.concatenate([d["q0"][chain][None], d["draws_q"][chain][:-1]])
+    states = stream_states(d["pre_rng"][chain])
+    kw = dict(TREE_KW.get(name, {}))
+    tune = int(d["tune"])
+    # draws with iteration index < 200 inside tuning use early_max_treedepth: replay them as tuning iterations
+    out = {}
+    early = np.arange(T) < min(tune, 200)
+    for sel, as_tune in ((early, True), (~early, False)):
+        if not sel.any():
+            continue
+        res = cm.nuts_run(q_prev[sel], states[sel].copy(), tune=1 if as_tune else 0, draws=0 if as_tune else 1,
+                          z=np.ascontiguousarray(d["z"][chain][sel][:, None, :]), mass="diag", var0=d["pre_var"][chain][sel],
+                          adapt_step_size=False, eps0=d["used_eps"][chain][sel], **kw)
+        out[as_tune] = (sel, res)
+    n = q_prev.shape[1]
+    dq = np.empty((T, n))
+    st = {}
+    for as_tune, (sel, res) in out.items():
+        dq[sel] = res.draws[:, 0]
+        for k, v in res.stats.items():
+            st.setdefault(k, np.zeros(T, dtype=v.dtype))[sel] = v[:, 0]
+    return dq, st
+
+
+def discrete_equal(st, d, chain):
+    ok = np.ones(len(st["depth"]), dtype=bool)
+    for k in DISCRETE:
+        if k == "reached_max_treedepth" :
+            continue
+        ok &= np.asarray(st[k]).astype(np.int64) == np.asarray(d["stat_" + k][chain]).astype(np.int64)
+    return ok

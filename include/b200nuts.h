@@ -93,7 +93,7 @@ typedef struct b200_nuts_cfg {
     int32_t mass_kind;           /* B200_MASS_*                                                       */
     int32_t momentum_source;     /* B200_MOMENTUM_*                                                   */
     int32_t store_warmup;        /* 1: outputs hold tune+draws iterations; 0: only the `draws` part   */
-    int32_t reserved0;
+    int32_t chain_offset;        /* global index of chain 0 of this call (multi-GPU shards): keys the Philox stream */
     double step_scale;           /* default 0.25; eps0 = step_scale / n**0.25 (base_hmc.py:161)       */
     double target_accept;        /* default 0.8                                                       */
     double gamma;                /* default 0.05                                                      */

@@ -55,7 +55,7 @@ class NutsCfg(C.Structure):
         ("mass_kind", C.c_int32),
         ("momentum_source", C.c_int32),
         ("store_warmup", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("chain_offset", C.c_int32),
         ("step_scale", C.c_double),
         ("target_accept", C.c_double),
         ("gamma", C.c_double),

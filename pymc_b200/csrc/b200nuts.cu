@@ -468,7 +468,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     P.eps0 = cfg->step_scale / std::pow((double)n, 0.25);  // base_hmc.py:161
     P.target = cfg->target_accept; P.gamma = cfg->gamma; P.kappa = cfg->k; P.t0 = cfg->t0;
     P.Emax = cfg->Emax; P.init_weight = cfg->mass_initial_weight;
-    P.philox_seed = cfg->philox_seed;
+    P.philox_seed = cfg->philox_seed; P.chain_offset = cfg->chain_offset;
     P.q0 = (const double*)s_q0.ptr(); P.var0 = (const double*)s_var0.ptr();
     P.mean0 = (const double*)s_mean0.ptr(); P.eps0c = (const double*)s_eps0.ptr(); P.z = (const double*)s_z.ptr();
     P.rng = (b200_pcg64*)s_rng.ptr(); P.draws_out = (double*)s_draws.ptr();

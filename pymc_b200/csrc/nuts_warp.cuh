@@ -33,7 +33,7 @@ constexpr int kMaxLevels = 12;  // pending-subtree levels (max_treedepth <= 12)
 
 struct NutsDev {
     int C, n, tune, draws, max_td, early_td, adapt_step, mass_kind, momentum_source, store_warmup;
-    int window, discard, hot_levels;
+    int window, discard, hot_levels, chain_offset;
     double eps0, target, gamma, kappa, t0, Emax, init_weight;
     unsigned long long philox_seed;
     const double* q0;     // [C][n]
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
             if (i < n) {
                 zz = (P.momentum_source == B200_MOMENTUM_HOST_BUFFER)
                          ? P.z[((long long)chain * Ttot + it) * n + i]
-                         : philox_normal(P.philox_seed, (uint32_t)chain, (uint32_t)it, (uint32_t)i);
+                         : philox_normal(P.philox_seed, (uint32_t)(chain + P.chain_offset), (uint32_t)it, (uint32_t)i);
             }
             p[k] = (1.0 / sqrt(var[k])) * zz;
         }

@@ -112,14 +112,16 @@ class CompiledModel:
                  mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
                  k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
-                 device_outputs=False, stats=True):
+                 device_outputs=False, stats=True, chain_offset=0):
         """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
 
         ``rng_states``: structured array (``_lib.PCG64_DTYPE``) of the chains' NumPy PCG64 step streams
         (see ``pymc_b200.rng``); updated in place.  ``z``: optional momentum noise [C, tune+draws, n]
         (NumPy ``Generator.normal`` for draw-parity with the reference); otherwise generated on device.
         ``device_outputs=True`` keeps draws/stats as torch CUDA tensors (no D2H copy)."""
-        q0 = _f64(q0).reshape(-1, self.n)
+        is_torch = lambda a: a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")  # noqa: E731
+        if not is_torch(q0):
+            q0 = _f64(q0).reshape(-1, self.n)
         Cn = q0.shape[0]
         Ttot = tune + draws
         T = Ttot if store_warmup else draws
@@ -130,6 +132,7 @@ class CompiledModel:
         cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT}[mass]
         cfg.momentum_source = _lib.MOMENTUM_DEVICE_PHILOX if z is None else _lib.MOMENTUM_HOST_BUFFER
         cfg.store_warmup = int(bool(store_warmup))
+        cfg.chain_offset = int(chain_offset)
         cfg.step_scale, cfg.target_accept, cfg.gamma, cfg.k, cfg.t0, cfg.Emax = (
             float(step_scale), float(target_accept), float(gamma), float(k), float(t0), float(Emax))
         cfg.mass_initial_weight = float(mass_initial_weight)
@@ -143,7 +146,14 @@ class CompiledModel:
 
             dev = torch.device("cuda", torch.cuda.current_device())
             mem = _lib.MEM_DEVICE
-            to_dev = lambda a: None if a is None else torch.as_tensor(_f64(a), device=dev)  # noqa: E731
+
+            def to_dev(a):  # NumPy -> HBM; torch CUDA tensors are used in place (inputs already resident)
+                if a is None:
+                    return None
+                if is_torch(a):
+                    return a.to(device=dev, dtype=torch.float64).contiguous()
+                return torch.as_tensor(_f64(a), device=dev)
+
             q0_b, var0_b, mean0_b, z_b = to_dev(q0), to_dev(var0), to_dev(mean0), to_dev(z)
             eps0_b = to_dev(eps0)
             rng_b = torch.as_tensor(rng_states.view(np.uint64).reshape(Cn, 4).view(np.int64), device=dev)

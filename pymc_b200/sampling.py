@@ -1,0 +1,178 @@
+"""Whole-run sampler: the drop-in for PyMC's external-NUTS seam (seam B4).
+
+``sample_b200_nuts`` mirrors the signature and return conventions of ``pymc.sampling.jax.sample_jax_nuts``
+(pymc/sampling/jax.py:495-517), which is how ``pm.sample(nuts_sampler=...)`` hands a whole run to an
+external sampler (``_sample_external_nuts``, pymc/sampling/mcmc.py:372-550).  All chains run in ONE
+call on the device; with ``torch.distributed`` initialised the chains are sharded over the ranks
+(``pymc_b200.parallel``).  PyMC / PyTensor / ArviZ are not importable in this image, so ``model`` is a
+``ModelSpec`` (pymc_b200.models) and the result is a light ``SampleResult`` with the same groups and
+names an ``InferenceData`` would carry (posterior, sample_stats, attrs); ``to_arviz()`` converts when
+ArviZ is present.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import rng as brng
+from .engine import CompiledModel
+from .models import ModelSpec
+
+
+class SamplingError(RuntimeError):
+    """pymc.exceptions.SamplingError: raised for "Bad initial energy" (hmc/base_hmc.py:205-224)."""
+
+
+# sample_stats names of the external samplers (pymc/sampling/jax.py:267-274, :376-391) from ours
+_STAT_RENAME = {
+    "diverging": "diverging",
+    "energy": "energy",
+    "depth": "tree_depth",
+    "tree_size": "n_steps",
+    "mean_tree_accept": "acceptance_rate",
+    "model_logp": "lp",
+    "step_size": "step_size",
+    "step_size_bar": "step_size_bar",
+    "energy_error": "energy_error",
+    "max_energy_error": "max_energy_error",
+    "index_in_trajectory": "index_in_trajectory",
+    "reached_max_treedepth": "reached_max_treedepth",
+}
+
+
+@dataclass
+class SampleResult:
+    posterior: dict  # rv name -> [chains, draws, ...]
+    sample_stats: dict  # stat name -> [chains, draws]
+    unconstrained: np.ndarray | None  # [chains, draws, n] (keep_untransformed)
+    warmup_posterior: dict | None = None
+    warmup_sample_stats: dict | None = None
+    attrs: dict = field(default_factory=dict)
+
+    def to_arviz(self):
+        import arviz as az  # optional
+
+        return az.from_dict(posterior=self.posterior, sample_stats=self.sample_stats, attrs=self.attrs)
+
+
+def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, jitter=True, logp_fn=None,
+                   jitter_max_retries=10):
+    """Per-chain start = the model's initial point (+ U(-1,1) jitter), re-drawn until logp is finite
+    (``_init_jitter``, pymc/sampling/mcmc.py:1695-1756; pymc/initial_point.py:328-340).
+
+    The reference draws the jitter with PyTensor RNG ops reseeded in graph-traversal order, which is
+    PyTensor-internal: parity with its jitter is unpinned; here each chain's jitter comes
+    from ``default_rng(jitter_seed)`` in raveled-vector order.  Pass ``initvals`` for exact starts."""
+    base = spec.initial_point()
+    q0 = np.empty((chains, spec.n))
+    for c in range(chains):
+        iv = None
+        if initvals is not None:
+            iv = initvals[c] if isinstance(initvals, (list, tuple)) else initvals
+        if isinstance(iv, np.ndarray):
+            q0[c] = iv
+            continue
+        start = base.copy()
+        if isinstance(iv, dict):
+            for v in spec.vars:
+                if v.name in iv:
+                    start[v.offset : v.offset + v.size] = np.ravel(iv[v.name])
+        g = np.random.default_rng(jitter_seeds[c])
+        q = start
+        for _ in range(jitter_max_retries + 1):
+            q = start + g.uniform(-1.0, 1.0, spec.n) if jitter else start
+            if logp_fn is None or not jitter:
+                break
+            if np.isfinite(logp_fn(q[None])[0][0]):
+                break
+        q0[c] = q
+    return q0
+
+
+def sample_b200_nuts(
+    draws: int = 1000,
+    *,
+    tune: int = 1000,
+    chains: int = 4,
+    target_accept: float = 0.8,
+    random_seed=None,
+    initvals=None,
+    jitter: bool = True,
+    model: ModelSpec | CompiledModel | None = None,
+    var_names=None,
+    nuts_kwargs: dict | None = None,
+    progressbar: bool = False,
+    quiet: bool = True,
+    keep_untransformed: bool = False,
+    chain_method: str = "vectorized",
+    idata_kwargs: dict | None = None,
+    compute_convergence_checks: bool = True,
+    discard_tuned_samples: bool = True,
+    momentum: str = "device",
+    nuts_sampler: str = "b200",
+) -> SampleResult:
+    """Draw samples from the posterior using the B200 NUTS engine (init = ``jitter+adapt_diag``).
+
+    Arguments follow ``sample_jax_nuts``.  ``nuts_kwargs`` accepts the ``pm.NUTS`` keywords
+    ``max_treedepth, early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size``.
+    ``momentum="numpy"`` draws the momentum normals from each chain's NumPy potential stream exactly like
+    the reference (host-generated, uploaded); ``"device"`` generates them on the GPU (Philox).
+    """
+    if model is None:
+        raise TypeError("model is required (a pymc_b200.models.ModelSpec or a CompiledModel)")
+    if chain_method not in ("vectorized", "parallel"):
+        raise ValueError("chain_method must be 'vectorized' or 'parallel'")
+    cm = model if isinstance(model, CompiledModel) else CompiledModel(model)
+    spec = cm.spec
+    nk = dict(nuts_kwargs or {})
+    nk.setdefault("target_accept", target_accept)
+
+    from . import parallel
+
+    lo, hi = parallel.my_chain_range(chains)
+    step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(random_seed, chains)
+    q0_all = initial_points(spec, chains, jitter_seeds, initvals, jitter, cm.logp_dlogp)
+    # init_nuts "jitter+adapt_diag": mean start point over ALL chains as the Welford prior mean (mcmc.py:1890-1894)
+    mean0 = np.broadcast_to(q0_all.mean(axis=0), (hi - lo, spec.n)).copy()
+    states = brng.pack_pcg64(step_rngs[lo:hi])
+    z = brng.momentum_noise(pot_rngs[lo:hi], tune + draws, spec.n) if momentum == "numpy" else None
+    seed_key = int(np.random.default_rng(jitter_seeds[0]).integers(2**63)) if z is None else 0
+
+    t0 = time.perf_counter()
+    res = cm.nuts_run(q0_all[lo:hi], states, tune=tune, draws=draws, mean0=mean0, z=z, philox_seed=seed_key,
+                      store_warmup=not discard_tuned_samples, mass="diag_adapt", chain_offset=lo, **nk)
+    sampling_time = time.perf_counter() - t0
+    bad = res.summary["bad_energy_at"]
+    if np.any(bad >= 0):
+        c = int(np.argmax(bad >= 0))
+        raise SamplingError(f"Bad initial energy in chain {lo + c} at iteration {int(bad[c])}: check any log "
+                            "probabilities that are inf or nan (model.debug())")
+    d_all, st_all = res.draws, res.stats
+    if parallel.world_size() > 1:
+        d_all, st_all = parallel.gather_chains(d_all, st_all, chains)
+
+    w = tune if not discard_tuned_samples else 0
+
+    def pack(dq, st):
+        post = spec.constrain(dq)
+        if var_names is not None:
+            post = {k: v for k, v in post.items() if k in var_names}
+        stats = {_STAT_RENAME[k]: (v.astype(bool) if v.dtype == np.uint8 else v) for k, v in st.items()}
+        return post, stats
+
+    post, stats = pack(d_all[:, w:], {k: v[:, w:] for k, v in st_all.items()})
+    out = SampleResult(post, stats, d_all[:, w:] if keep_untransformed else None)
+    if w:
+        out.warmup_posterior, out.warmup_sample_stats = pack(d_all[:, :w], {k: v[:, :w] for k, v in st_all.items()})
+    out.attrs = {"sampling_time": sampling_time, "tuning_steps": tune, "inference_library": "pymc_b200",
+                 "kernel_ms": res.kernel_ms, "grad_evals": int(st_all["tree_size"].sum())}
+    if compute_convergence_checks and chains > 1 and draws >= 8:
+        from . import diagnostics
+
+        x = d_all[:, w:]
+        out.attrs["ess_bulk_min"] = float(np.nanmin(diagnostics.ess_bulk(x)))
+        out.attrs["rhat_max"] = float(np.nanmax(diagnostics.rhat(x)))
+        out.attrs["divergences"] = int(stats["diverging"].sum())
+    return out

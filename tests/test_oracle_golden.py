@@ -1,0 +1,81 @@
+"""CPU: oracle/nuts_numpy.py against the committed golden vectors (made by oracle/make_golden.py from the
+reference's own code).  Fixed-step cases must reproduce whole chains; adaptive (chaotic) cases are
+replayed draw by draw from the golden pre-draw state, which is robust to BLAS kernels of another CPU."""
+import numpy as np
+import pytest
+
+from b200_helpers import SPEC_OF, TREE_KW
+from oracle import logp_numpy, nuts_numpy
+
+
+def _oracle(spec, f, var, adapt=False, **kw):
+    return nuts_numpy.Oracle(f, nuts_numpy.DiagMass(var, adapt=adapt), adapt_step_size=False, **kw)
+
+
+def _gen_from_state(state_u64x4):
+    g = np.random.default_rng(0)
+    st = g.bit_generator.state
+    st["state"]["state"] = (int(state_u64x4[0]) << 64) | int(state_u64x4[1])
+    st["state"]["inc"] = (int(state_u64x4[2]) << 64) | int(state_u64x4[3])
+    st["has_uint32"], st["uinteger"] = 0, 0
+    g.bit_generator.state = st
+    return g
+
+
+@pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed"])
+def test_fixed_step_chains_reproduce_golden(golden, name):
+    d = golden(name)
+    spec = SPEC_OF[name]()
+    f = logp_numpy.make_logp(spec)
+    for c in range(len(d["seeds"])):
+        o = _oracle(spec, f, d["var"][c])
+        o.da = nuts_numpy.DualAveraging(float(d["used_eps"][c][0]))
+        o.rng, o.tune = _gen_from_state(d["pre_rng"][c][0]), False
+        qs, st = o.run(d["q0"][c], 0, int(d["draws"]), z=d["z"][c])
+        assert np.array_equal(st["tree_size"], d["stat_tree_size"][c])
+        assert np.array_equal(st["index_in_trajectory"], d["stat_index_in_trajectory"][c])
+        assert np.max(np.abs(qs - d["draws_q"][c])) <= 1e-9
+        assert np.max(np.abs(st["energy"] - d["stat_energy"][c])) <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_small_adapt", "radon_adapt"])
+def test_single_draw_replay_of_adaptive_golden(golden, name):
+    d = golden(name)
+    spec = SPEC_OF[name]()
+    f = logp_numpy.make_logp(spec)
+    tune, T = int(d["tune"]), int(d["tune"]) + int(d["draws"])
+    sel = range(0, T, 7 if name == "radon_adapt" else 3)
+    q_prev = np.concatenate([d["q0"][0][None], d["draws_q"][0][:-1]])
+    bad = 0
+    for t in sel:
+        o = _oracle(spec, f, d["pre_var"][0][t], **TREE_KW.get(name, {}))
+        o.da = nuts_numpy.DualAveraging(float(d["used_eps"][0][t]))
+        o.rng = _gen_from_state(d["pre_rng"][0][t])
+        o.tune = t < tune
+        o.iter_count = t
+        o.adapt_step_size = False
+        # the step size of a tuning draw is exp(log_step); with adaptation off current() reads log_bar == log_step here
+        q, st = o.draw(q_prev[t], z=d["z"][0][t])
+        same = (st["tree_size"] == d["stat_tree_size"][0][t]) and (st["depth"] == d["stat_depth"][0][t])
+        if not same:
+            bad += 1
+            continue
+        assert np.max(np.abs(q - d["draws_q"][0][t])) <= 1e-6
+        assert st["diverging"] == bool(d["stat_diverging"][0][t])
+    assert bad <= max(1, len(sel) // 50)
+
+
+@pytest.mark.parametrize("name", ["eight_schools_warm_adapt", "radon_warm_adapt"])
+def test_adaptation_prefix_reproduces_golden(golden, name):
+    """Dual averaging + Welford bookkeeping: first 120 iterations (covers discard window and first switch)."""
+    d = golden(name)
+    spec = SPEC_OF[name]()
+    f = logp_numpy.make_logp(spec)
+    mass = nuts_numpy.DiagMass(d["init_var"][0], adapt=True, initial_mean=d["q0"][0].copy(), initial_weight=10)
+    o = nuts_numpy.Oracle(f, mass, step_scale=float(d["step_scale"]))
+    o.rng = _gen_from_state(d["pre_rng"][0][0])
+    T = 120
+    qs, st = o.run(d["q0"][0], T, 0, z=d["z"][0][:T])
+    assert np.array_equal(st["tree_size"], d["stat_tree_size"][0][:T])
+    assert np.max(np.abs(st["step_size"] - d["stat_step_size"][0][:T]) / d["stat_step_size"][0][:T]) <= 1e-9
+    assert np.max(np.abs(qs - d["draws_q"][0][:T])) <= 1e-7

@@ -112,13 +112,15 @@ class CompiledModel:
                  mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
                  k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
-                 device_outputs=False, stats=True, chain_offset=0):
+                 device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False):
         """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
 
         ``rng_states``: structured array (``_lib.PCG64_DTYPE``) of the chains' NumPy PCG64 step streams
         (see ``pymc_b200.rng``); updated in place.  ``z``: optional momentum noise [C, tune+draws, n]
         (NumPy ``Generator.normal`` for draw-parity with the reference); otherwise generated on device.
-        ``device_outputs=True`` keeps draws/stats as torch CUDA tensors (no D2H copy)."""
+        ``device_outputs=True`` keeps draws/stats as torch CUDA tensors (no D2H copy).
+        ``pinned_outputs=True`` returns host arrays backed by a per-model pool of pinned (page-locked) buffers
+        that is REUSED by the next call of the same shape (fast D2H; copy what you want to keep)."""
         is_torch = lambda a: a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")  # noqa: E731
         if not is_torch(q0):
             q0 = _f64(q0).reshape(-1, self.n)
@@ -168,8 +170,23 @@ class CompiledModel:
             z_b = None if z is None else _f64(z).reshape(Cn, Ttot, self.n)
             eps0_b = None if eps0 is None else np.broadcast_to(_f64(eps0), (Cn,)).copy()
             rng_b = rng_states
-            draws_b = np.empty((Cn, T, self.n))
-            mk = lambda shape, dt: np.zeros(shape, dtype=dt)  # noqa: E731
+            if pinned_outputs:
+                pool = self.__dict__.setdefault("_pinned_pool", {})
+
+                def mk(shape, dt, _tag=[0]):  # noqa: B006
+                    _tag[0] += 1
+                    key = (_tag[0], tuple(shape), np.dtype(dt).str)
+                    if key not in pool:
+                        import torch
+
+                        tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
+                        pool[key] = torch.zeros(tuple(shape), dtype=tdt[dt], pin_memory=True).numpy()
+                    return pool[key]
+
+                draws_b = mk((Cn, T, self.n), np.float64)
+            else:
+                draws_b = np.empty((Cn, T, self.n))
+                mk = lambda shape, dt: np.zeros(shape, dtype=dt)  # noqa: E731
 
         st, st_arr = _lib.Stats(), {}
         if stats:

@@ -153,10 +153,17 @@ def test_nuts_adaptation_from_warm_state(compiled, golden, name):
     st = {k: v[0] for k, v in res.stats.items()}
     ok = discrete_equal(st, d, 0)
     first_bad = int(np.argmin(ok)) if not ok.all() else len(ok)
-    assert first_bad >= 150, f"{name}: diverged from the reference at draw {first_bad}"
-    m = slice(0, first_bad)
-    assert relerr(st["step_size"][m], d["stat_step_size"][0][m]) <= 1e-6
-    assert np.max(np.abs(res.draws[0][m] - d["draws_q"][0][m])) <= 1e-6
+    # adaptation feeds the step size back into the dynamics, so ulp differences grow exponentially even from a
+    # warm state (the error curve is smooth: no jump at the Welford window switches at t=102 and t=203)
+    assert first_bad >= 120, f"{name}: diverged from the reference at draw {first_bad}"
+    m = slice(0, 100)
+    assert relerr(st["step_size"][m], d["stat_step_size"][0][m]) <= 1e-5
+    assert np.max(np.abs(res.draws[0][m] - d["draws_q"][0][m])) <= 1e-4
+    m = slice(0, 30)
+    assert relerr(st["step_size"][m], d["stat_step_size"][0][m]) <= 1e-8
+    assert np.max(np.abs(res.draws[0][m] - d["draws_q"][0][m])) <= 1e-7
+    if first_bad == len(ok):  # still on the reference's path at the end: the adapted mass matrix agrees
+        assert relerr(res.summary["final_var"][0], d["final_var"][0]) <= 1e-2
 
 
 @pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_adapt"])
@@ -234,7 +241,8 @@ def test_sampler_statistics_std_normal(compiled):
     acc = res.stats["mean_tree_accept"].mean()
     assert 0.7 < acc < 0.92, acc
     assert res.stats["diverging"].sum() == 0
-    assert np.all(np.abs(res.summary["final_var"] - 1.0) < 0.6)
+    fv = res.summary["final_var"]  # Welford over ~100-200 draws: sd ~ 0.12 per entry
+    assert abs(fv.mean() - 1.0) < 0.03 and np.all(np.abs(fv - 1.0) < 0.9)
 
 
 def test_radon_full_size_run_properties(compiled):
@@ -264,3 +272,43 @@ def test_radon_full_size_run_properties(compiled):
     B = mu_a.mean(1).var() * mu_a.shape[1]
     W = mu_a.var(1).mean()
     assert B / W < 3.0
+
+
+def test_reference_sampler_drives_cuda_logp_through_seam_b1(compiled):
+    """Seam B1: the (restated) reference NUTS calling the CUDA logp/grad one point at a time gives the same
+    chain as with the NumPy logp -- correctness of a1 behind the reference's own tree builder."""
+    from oracle import logp_numpy, nuts_numpy
+    from pymc_b200.step import B200LogpDlogp
+
+    cm = compiled("eight_schools_fixed")
+    f_np = logp_numpy.make_logp(cm.spec)
+    f_cu = B200LogpDlogp(cm)
+    outs = []
+    for f in (f_np, f_cu._pytensor_function):
+        o = nuts_numpy.Oracle(f, nuts_numpy.DiagMass(np.ones(cm.n)), adapt_step_size=False)
+        o.setup_chain(np.random.default_rng(3))
+        o.tune = False
+        outs.append(o.run(np.zeros(cm.n), 0, 12))
+    assert np.array_equal(outs[0][1]["tree_size"], outs[1][1]["tree_size"])
+    assert np.max(np.abs(outs[0][0] - outs[1][0])) <= 1e-9
+
+
+def test_sample_b200_nuts_public_api(compiled):
+    """Seam B4: signature/return conventions of sample_jax_nuts; seed reproducibility (test_mcmc_external.py:83)."""
+    import pymc_b200
+    from pymc_b200 import models
+
+    spec = models.eight_schools()
+    a = pymc_b200.sample_b200_nuts(200, tune=300, chains=8, random_seed=11, model=spec, keep_untransformed=True)
+    b = pymc_b200.sample_b200_nuts(200, tune=300, chains=8, random_seed=11, model=spec, keep_untransformed=True)
+    assert set(a.posterior) == {"mu", "tau", "theta_t"}
+    assert a.posterior["mu"].shape == (8, 200) and a.posterior["theta_t"].shape == (8, 200, 8)
+    assert {"diverging", "energy", "tree_depth", "n_steps", "acceptance_rate", "lp", "step_size"} <= set(a.sample_stats)
+    assert {"sampling_time", "tuning_steps"} <= set(a.attrs) and a.attrs["tuning_steps"] == 300
+    assert np.array_equal(a.unconstrained, b.unconstrained)
+    assert np.all(a.posterior["tau"] > 0)
+    # posterior sanity vs the well-known Eight Schools answer (mu ~ 4.4, tau median ~ 2.7)
+    assert 3.0 < a.posterior["mu"].mean() < 6.0
+    c = pymc_b200.sample_b200_nuts(50, tune=100, chains=2, random_seed=5, model=spec, momentum="numpy",
+                                   discard_tuned_samples=False)
+    assert c.warmup_posterior["mu"].shape == (2, 100) and c.posterior["mu"].shape == (2, 50)

@@ -182,12 +182,13 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic():
-    """dram bytes per launch from the committed ncu capture of this command (profiles/), else None."""
+def ncu_traffic(evals_per_launch):
+    """DRAM bytes per launch: bytes/grad-eval measured by ncu on a shorter launch of the same kernel
+    (profiles/r1_traffic.json) x the grad-evals of this launch; None if no capture is committed."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.isfile(p):
         try:
-            return json.load(open(p)).get("nuts_warp_kernel_dram_bytes_per_launch")
+            return float(json.load(open(p))["dram_bytes_per_grad_eval"]) * evals_per_launch
         except Exception:
             return None
     return None
@@ -309,7 +310,8 @@ def b200_arm(args):
         if _lib.load().b200_measure_fp64_tflops(ctypes.byref(tf)) == 0:
             fp64 = tf.value
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": how, "kernel": "nuts_warp_kernel<RadonModel,6>",
+                "traffic": ncu_traffic(all_evals / args.steps), "peak_source": how,
+                "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch", "kernel": "nuts_warp_kernel<RadonModel,6>",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
                 "note": "observed data is staged once per CTA into shared memory (bulk TMA) and the chain state lives in "
                         "registers/shared memory, so DRAM traffic is far below the algorithmic bytes; the binding pipe is fp64",

@@ -40,7 +40,7 @@ __device__ __forceinline__ double sigmoid(double x) {
 // logprob/transforms.py:880-891.  `x` must be exp(z) (passed in so callers can share the exp).
 __device__ __forceinline__ void halfcauchy_log(double z, double x, double beta, double log_beta,
                                                double& val, double& dz) {
-    const double t = x / beta;
+    const double t = x * (1.0 / beta);
     const double u = t * t;
     val = (0.69314718055994530942 - 1.1447298858494001741 /* log pi */) - log_beta - log1p(u) + z;
     dz = 1.0 - 2.0 * u / (1.0 + u);
@@ -64,6 +64,46 @@ __device__ __forceinline__ void warp_sum_n(double (&x)[N]) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] += __shfl_xor_sync(B200_FULL_MASK, x[i], o);
     }
+}
+
+// All-reduce of N <= 8 values in 9 + N double-shuffles instead of 5 N: a reduce-scatter over lane bits
+// 4,3,2 (each step halves the values a lane carries), a butterfly over bits 1,0, then one broadcast per
+// value.  Every lane receives the broadcast of the same lane's total, so results are warp-uniform bits.
+template <int N>
+__device__ __forceinline__ void warp_sum_bcast_n(double (&x)[N], int lane) {
+    static_assert(N >= 1 && N <= 8, "warp_sum_bcast_n handles up to 8 values");
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i < N) ? x[i] : 0.0;
+    double w[4], u[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+            w[i] = keep + __shfl_xor_sync(B200_FULL_MASK, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double send = up ? w[i] : w[i + 2], keep = up ? w[i + 2] : w[i];
+            u[i] = keep + __shfl_xor_sync(B200_FULL_MASK, send, 8);
+        }
+    }
+    double t;
+    {
+        const bool up = lane & 4;
+        const double send = up ? u[0] : u[1], keep = up ? u[1] : u[0];
+        t = keep + __shfl_xor_sync(B200_FULL_MASK, send, 4);
+    }
+    t += __shfl_xor_sync(B200_FULL_MASK, t, 2);
+    t += __shfl_xor_sync(B200_FULL_MASK, t, 1);
+    // lane holds the total of value j = 4*bit4 + 2*bit3 + bit2
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        x[j] = __shfl_sync(B200_FULL_MASK, t, ((j & 4) ? 16 : 0) | ((j & 2) ? 8 : 0) | ((j & 1) ? 4 : 0));
 }
 
 // ---------------------------------------------------------------------------------------------

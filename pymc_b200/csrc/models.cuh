@@ -125,10 +125,10 @@ struct RadonModel {
         const int32_t* rows = seg + P.M * 32;
         const int J = P.J;
         const double mu_a = q_s[0], mu_b = q_s[2];
-        // one exp() for the warp: lanes 0,1,2 take log sigma_a, log sigma_b, log eps
-        const int zi = (lane % 3 == 0) ? 1 : (lane % 3 == 1 ? 3 : 4 + 2 * J);
+        // one exp() for the warp: lanes 0,1,2 take log sigma_a, log sigma_b, log eps; lane 3 takes -2 log eps
+        const int zi = ((lane & 3) == 0) ? 1 : ((lane & 3) == 1 ? 3 : 4 + 2 * J);
         const double zl = q_s[zi];
-        const double ex = exp(zl);
+        const double ex = exp((lane & 3) == 3 ? -2.0 * zl : zl);
         // HalfCauchy(5)+Jacobian of the same three, one log1p() for the warp
         double hc_l, dhc_l;
         halfcauchy_log(zl, ex, 5.0, 1.6094379124341002818, hc_l, dhc_l);
@@ -139,7 +139,7 @@ struct RadonModel {
         const double dhca = __shfl_sync(B200_FULL_MASK, dhc_l, 0), dhcb = __shfl_sync(B200_FULL_MASK, dhc_l, 1),
                      dhce = __shfl_sync(B200_FULL_MASK, dhc_l, 2);
         const double leps = q_s[4 + 2 * J];
-        const double inv_e2 = 1.0 / (eps * eps);
+        const double inv_e2 = __shfl_sync(B200_FULL_MASK, ex, 3);  // 1 / eps^2 = exp(-2 log eps)
         const double sa_ie2 = sa * inv_e2, sb_ie2 = sb * inv_e2;
 
         // acc: S2, sum Ga, sum a*Ga, sum Gb, sum b*Gb, sum a^2, sum b^2   (Ga/Gb raw: sums of residuals)
@@ -158,11 +158,12 @@ struct RadonModel {
 #pragma unroll 4
             for (int k = 0; k < len; ++k) {
                 const double2 d = row[k * 32];
-                double r = d.y - fma(be, d.x, al);
-                r = (k < cnt) ? r : 0.0;  // padding contributes exact zeros
-                S2 = fma(r, r, S2);
-                Ga += r;
-                Gb = fma(r, d.x, Gb);
+                const double r = d.y - fma(be, d.x, al);
+                if (k < cnt) {  // padding of the row is skipped (predicated, no branch)
+                    S2 = fma(r, r, S2);
+                    Ga += r;
+                    Gb = fma(r, d.x, Gb);
+                }
             }
             acc[0] += S2;
             if (live) {  // county finished: its two gradient entries are complete
@@ -184,7 +185,7 @@ struct RadonModel {
             acc[5] = fma(ae, ae, acc[5]);
             acc[6] = fma(bb, bb, acc[6]);
         }
-        warp_sum_n(acc);
+        warp_sum_bcast_n(acc, lane);
         const double S = 1.0e4;  // sigma = 100**2
         if (lane == 0) {
             g_s[0] = fma(inv_e2, acc[1], -mu_a * (1.0 / (S * S)));
@@ -193,7 +194,7 @@ struct RadonModel {
             g_s[3] = fma(sb_ie2, acc[4], dhcb);
             g_s[4 + 2 * J] = dhce + fma(acc[0], inv_e2, -(double)P.n_obs);
         }
-        const double za = mu_a / S, zb = mu_b / S;
+        const double za = mu_a * 1.0e-4, zb = mu_b * 1.0e-4;
         const double log_S = 9.2103403719761827361;  // log 1e4
         double lp = (-0.5 * za * za - B200_HALF_LOG_2PI - log_S) + (-0.5 * zb * zb - B200_HALF_LOG_2PI - log_S);
         lp += hca + hcb + hce;

@@ -56,8 +56,11 @@ __host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
     return (long long)(G_STACK + 4 * levels) * NP;
 }
 // shared memory per warp (bytes): q, g, hot stack levels (level 0: 2 vectors, others: 4), scalars
+#ifndef B200_SUBTREE_SMEM
+#define B200_SUBTREE_SMEM 0  // 1: left.p / p_sum / proposal q of the subtree under construction live in shared memory
+#endif                       //    (frees 6*NPL registers per lane -> more resident warps); 0: in registers
 __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot) {
-    const int vecs = 2 + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
+    const int vecs = 2 + (B200_SUBTREE_SMEM ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
     return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double);
 }
 
@@ -91,7 +94,21 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     double* ws = reinterpret_cast<double*>(smem_raw + data_bytes + wib * nuts_warp_smem_bytes(NP, hot));
     double* q_s = ws;
     double* g_s = ws + NP;
+#if B200_SUBTREE_SMEM
+    double* lp_s = ws + 2 * NP + lane;
+    double* ps_s = ws + 3 * NP + lane;
+    double* pq_s = ws + 4 * NP + lane;
+    double* hot_base = ws + 5 * NP;
+#define LP(k) lp_s[32 * (k)]
+#define PS(k) ps_s[32 * (k)]
+#define PQ(k) pq_s[32 * (k)]
+#else
     double* hot_base = ws + 2 * NP;
+    double lp_r[NPL], ps_r[NPL], pq_r[NPL];
+#define LP(k) lp_r[k]
+#define PS(k) ps_r[k]
+#define PQ(k) pq_r[k]
+#endif
     double* sc_logw = hot_base + (hot > 0 ? 2 + 4 * (hot - 1) : 0) * NP;
     double* sc_pe = sc_logw + kMaxLevels;
     double* sc_plogp = sc_pe + kMaxLevels;
@@ -110,7 +127,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     const int T_out = P.store_warmup ? Ttot : P.draws;
 
     // ---- per-chain persistent state ---------------------------------------------------------------
-    double var[NPL], p[NPL], lp[NPL], ps[NPL], pq[NPL];
+    double var[NPL], p[NPL];
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
         const int i = lane + 32 * k;
@@ -179,19 +196,19 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
         // ---- _Tree.__init__ (nuts.py:292-332): both edges, proposal and p_sum are the start state ----
         double* Lq = gvec(G_LQ); double* Lp = gvec(G_LP); double* Lg = gvec(G_LG);
         double* Rq = gvec(G_RQ); double* Rp = gvec(G_RP); double* Rg = gvec(G_RG);
-        double* PS = gvec(G_PS); double* PQ = gvec(G_PQ); double* NEARP = gvec(G_NEARP);
+        double* PSv = gvec(G_PS); double* PQv = gvec(G_PQ); double* NEARP = gvec(G_NEARP);
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + 32 * k;
             const double qi = q_s[i], gi = g_s[i];
-            Lq[i] = qi; Rq[i] = qi; PQ[i] = qi;
+            Lq[i] = qi; Rq[i] = qi; PQv[i] = qi;
             Lg[i] = gi; Rg[i] = gi;
-            Lp[i] = p[k]; Rp[i] = p[k]; PS[i] = p[k];
+            Lp[i] = p[k]; Rp[i] = p[k]; PSv[i] = p[k];
         }
         int L_idx = 0, R_idx = 0;
         double m_logw = 0.0, m_pe = E0, m_plogp = logp0;
         int m_pidx = 0;
-        double log_accept = -INFINITY, max_de = 0.0;
+        double accept_sum = 0.0, max_de = 0.0;  // sum of min(1, exp(-dE)): exp(log_accept_sum) of nuts.py:415 without the log
         int n_prop = 0, depth = 0;
         bool diverged = false, turned = false, hit_max = false;
 
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 ++n_prop;
                 double dE = E - E0;
                 if (isnan(dE)) dE = INFINITY;
-                log_accept = logaddexp(log_accept, dE > 0 ? -dE : 0.0);
+                accept_sum += (dE > 0) ? exp(-dE) : 1.0;
                 if (fabs(dE) > fabs(max_de)) max_de = dE;
                 if (!(dE < P.Emax)) {
                     sub_div = true;
@@ -252,9 +269,9 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 // the leaf as a height-0 subtree: left = right = p_sum = p, proposal = itself
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    lp[k] = p[k];
-                    ps[k] = p[k];
-                    pq[k] = q_s[lane + 32 * k];
+                    LP(k) = p[k];
+                    PS(k) = p[k];
+                    PQ(k) = q_s[lane + 32 * k];
                 }
                 c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
 
@@ -270,42 +287,50 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                         for (int k = 0; k < NPL; ++k) {
                             const int i = lane + 32 * k;
                             const double tp = t_ps[i];
-                            const double s = tp + ps[k];
+                            const double s = tp + PS(k);
                             dots[0] = fma(s, var[k] * tp, dots[0]);
                             dots[1] = fma(s, var[k] * p[k], dots[1]);
-                            lp[k] = tp;
-                            ps[k] = s;
+                            LP(k) = tp;
+                            PS(k) = s;
                         }
+                        double d2[2] = {dots[0], dots[1]};
+                        warp_sum_n(d2);
+                        dots[0] = d2[0]; dots[1] = d2[1];
                         dots[2] = dots[3] = dots[4] = dots[5] = 1.0;
                     } else {
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
                             const int i = lane + 32 * k;
                             const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
-                            const double s = tp + ps[k];
+                            const double s = tp + PS(k);
                             const double vl = var[k] * tl, vr = var[k] * p[k];
                             dots[0] = fma(s, vl, dots[0]);
                             dots[1] = fma(s, vr, dots[1]);
-                            const double s1 = tp + lp[k];  // tree1.p_sum + tree2.left.p
+                            const double s1 = tp + LP(k);  // tree1.p_sum + tree2.left.p
                             dots[2] = fma(s1, vl, dots[2]);
-                            dots[3] = fma(s1, var[k] * lp[k], dots[3]);
-                            const double s2 = tr + ps[k];  // tree1.right.p + tree2.p_sum
+                            dots[3] = fma(s1, var[k] * LP(k), dots[3]);
+                            const double s2 = tr + PS(k);  // tree1.right.p + tree2.p_sum
                             dots[4] = fma(s2, var[k] * tr, dots[4]);
                             dots[5] = fma(s2, vr, dots[5]);
-                            lp[k] = tl;
-                            ps[k] = s;
+                            LP(k) = tl;
+                            PS(k) = s;
                         }
                     }
-                    warp_sum_n(dots);
+                    if (h) warp_sum_bcast_n(dots, lane);
                     const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
                                       (dots[4] <= 0) || (dots[5] <= 0);
+                    // logw = logaddexp(t, c) = max + log1p(e), e = exp(-|c - t|); the pick  log(u) < c - logw  is
+                    // u * (1 + e) < (c >= t ? 1 : e): same decision without evaluating log(u)
                     const double t_logw = sc_logw[h];
-                    const double logw = logaddexp(t_logw, c_logw);
+                    const double dlw = c_logw - t_logw;
+                    const double e_w = exp(-fabs(dlw));
+                    const double logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
+                                                     : (isnan(dlw) ? c_logw + t_logw : fmax(c_logw, t_logw) + log1p(e_w));
                     const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
-                    if (!(log(u) < c_logw - logw)) {     // keep tree1's proposal
+                    if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                         const double* t_pq = lvl(h, 3);
 #pragma unroll
-                        for (int k = 0; k < NPL; ++k) pq[k] = t_pq[lane + 32 * k];
+                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + 32 * k];
                         c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
                     }
                     c_logw = logw;
@@ -323,8 +348,8 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
                             const int i = lane + 32 * k;
-                            s_ps[i] = ps[k];
-                            s_pq[i] = pq[k];
+                            s_ps[i] = PS(k);
+                            s_pq[i] = PQ(k);
                         }
                     } else {
                         double* s_lp = lvl(h, 0);
@@ -332,10 +357,10 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
                             const int i = lane + 32 * k;
-                            s_lp[i] = lp[k];
+                            s_lp[i] = LP(k);
                             s_rp[i] = p[k];
-                            s_ps[i] = ps[k];
-                            s_pq[i] = pq[k];
+                            s_ps[i] = PS(k);
+                            s_pq[i] = PQ(k);
                         }
                     }
                     if (lane == 0) {
@@ -367,12 +392,15 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
             // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
             {
                 const double u = rng.next_double();
-                if (log(u) < c_logw - m_logw) {
+                const double dlw = c_logw - m_logw;
+                const double e_w = exp(-fabs(dlw));
+                if (dlw >= 0.0 || u < e_w) {  // log(u) < c_logw - m_logw
 #pragma unroll
-                    for (int k = 0; k < NPL; ++k) PQ[lane + 32 * k] = pq[k];
+                    for (int k = 0; k < NPL; ++k) PQv[lane + 32 * k] = PQ(k);
                     m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
                 }
-                m_logw = logaddexp(c_logw, m_logw);
+                m_logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
+                                      : (isnan(dlw) ? c_logw + m_logw : fmax(c_logw, m_logw) + log1p(e_w));
             }
             // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
             {
@@ -381,20 +409,20 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + 32 * k;
-                    const double so = PS[i], fp = FARP[i], np_ = NEARP[i];
-                    const double s = so + ps[k];
-                    PS[i] = s;
+                    const double so = PSv[i], fp = FARP[i], np_ = NEARP[i];
+                    const double s = so + PS(k);
+                    PSv[i] = s;
                     const double vf = var[k] * fp, vw = var[k] * p[k];
                     dots[0] = fma(s, vf, dots[0]);
                     dots[1] = fma(s, vw, dots[1]);
-                    const double a = so + lp[k];   // old p_sum + (new subtree's edge adjacent to the old tree).p
+                    const double a = so + LP(k);   // old p_sum + (new subtree's edge adjacent to the old tree).p
                     dots[2] = fma(a, vf, dots[2]);
-                    dots[3] = fma(a, var[k] * lp[k], dots[3]);
-                    const double b = np_ + ps[k];  // (old tree's edge adjacent to the new subtree).p + new p_sum
+                    dots[3] = fma(a, var[k] * LP(k), dots[3]);
+                    const double b = np_ + PS(k);  // (old tree's edge adjacent to the new subtree).p + new p_sum
                     dots[4] = fma(b, var[k] * np_, dots[4]);
                     dots[5] = fma(b, vw, dots[5]);
                 }
-                warp_sum_n(dots);
+                warp_sum_bcast_n(dots, lane);
                 if ((dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) || (dots[4] <= 0) ||
                     (dots[5] <= 0)) {
                     turned = true;
@@ -405,15 +433,15 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
         if (d_iter == maxd) hit_max = !tuning;  // for/else of nuts.py:220-221
 
         // ---- the accepted position becomes the chain state -------------------------------------------
-        const double accept = exp(log_accept) / n_prop;  // nuts.py:479
+        const double accept = accept_sum / n_prop;  // nuts.py:479
         const bool rec = P.store_warmup || !tuning;
         const int t_out = P.store_warmup ? it : it - P.tune;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + 32 * k;
-            const double qi = PQ[i];
+            const double qi = PQv[i];
             q_s[i] = qi;
-            pq[k] = qi;
+            PQ(k) = qi;
             if (rec && i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = qi;
         }
         // ---- step_adapt.update (step_sizes.py:66-78); products/sums kept unfused like the Python scalars
@@ -435,7 +463,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + 32 * k;
-                    const double x = pq[k];
+                    const double x = PQ(k);
                     double mean = fm[i];
                     double d0 = x - mean;
                     mean = __dadd_rn(mean, d0 / fg_n);

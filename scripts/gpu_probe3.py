@@ -14,7 +14,7 @@ ms, _ = _lib.last_kernel_ms()
 tag = os.environ.get("B200_LIB", "default")[-14:]
 print(f"[{tag}] leapfrog: {C*1000/ms/1e3:.1f} M evals/s")
 sr, pr, _ = brng.chain_generators(123, C)
-for wpb, hot in ((4, 2), (4, 1), (4, 3)):
+for wpb, hot in ((4, 0), (4, 1), (4, 2), (8, 1)):
     os.environ["B200_NUTS_WPB"] = str(wpb); os.environ["B200_NUTS_HOT"] = str(hot)
     res = cm.nuts_run(q0, brng.pack_pcg64(sr), tune=0, draws=40, mass="diag", adapt_step_size=False, eps0=np.full(C, 1e-5),
                       max_treedepth=5, early_max_treedepth=5, philox_seed=3)

@@ -134,5 +134,28 @@ def main():
          adapt=True, nuts_kwargs={"max_treedepth": 6, "early_max_treedepth": 4})
 
 
+def team_cases():
+    """Cases for the chain-per-CTA (team) kernels: std_normal n=300 and stochastic volatility."""
+    rng = np.random.default_rng(21)
+    q0s = [rng.standard_normal(300) for _ in range(2)]
+    case("std_normal_team_fixed", "std_normal", {"n": 300}, q0s, [17, 18], tune=0, draws=20, adapt=False)
+    # stochastic volatility, small T: cold adaptive run, then fixed replay from its end state
+    sv = models.stochvol(T=100, seed=4)
+    q0s = [sv.initial_point() + rng.uniform(-1, 1, sv.n)]
+    a = case("stochvol_small_adapt", "stochvol", {"T": 100, "seed": 4}, q0s, [701], tune=300, draws=40, adapt=True)
+    case("stochvol_small_fixed", "stochvol", {"T": 100, "seed": 4}, [a["draws_q"][0, -1]], [702], tune=0, draws=30,
+         adapt=False, var=a["final_var"], eps=a["final_step_size"])
+    # full size (T=3000, n=3003): warm up with the reference, keep only a short fixed replay
+    sv = models.stochvol()
+    q0 = sv.initial_point() + rng.uniform(-1, 1, sv.n)
+    b = run_reference(sv, q0, seed=703, tune=250, draws=1, adapt=True)
+    print("stochvol full warm-up: evals", int(b[1]["tree_size"].sum()), "final eps", b[3])
+    case("stochvol_fixed", "stochvol", {}, [b[0][-1]], [704], tune=0, draws=6, adapt=False, var=np.array([b[2]]),
+         eps=np.array([b[3]]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "team":
+        team_cases()
+        raise SystemExit(0)
     main()

@@ -52,6 +52,7 @@ struct b200_model {
     StdNormalModel::Params std_normal{};
     EightSchoolsModel::Params eight{};
     RadonModel::Params radon{};
+    StochVolModel::Params stochvol{};
     ~b200_model() { for (void* p : owned) cudaFree(p); }
 };
 
@@ -152,6 +153,16 @@ static int prepare_eight(b200_model* m, const b200_model_desc* d) {
     return 0;
 }
 
+static int prepare_stochvol(b200_model* m, const b200_model_desc* d) {
+    const int T = (int)d->n_obs;
+    if (T < 2 || !d->y) return fail("stochvol: missing data");
+    if (d->n != T + 3) return fail("stochvol: n=%d but T+3=%d", d->n, T + 3);
+    std::vector<double> y2(T);
+    for (int t = 0; t < T; ++t) y2[t] = d->y[t] * d->y[t];
+    m->stochvol.T = T;
+    return upload(m, y2, &m->stochvol.y2);
+}
+
 extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) {
     if (!desc || !out) return fail("b200_model_create: null argument");
     if (desc->n <= 0) return fail("b200_model_create: n must be positive");
@@ -165,6 +176,7 @@ extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) 
         case B200_MODEL_STD_NORMAL: m->std_normal.n = desc->n; break;
         case B200_MODEL_EIGHT_SCHOOLS: rc = prepare_eight(m, desc); break;
         case B200_MODEL_RADON: rc = prepare_radon(m, desc); break;
+        case B200_MODEL_STOCHVOL: rc = prepare_stochvol(m, desc); break;
         default: rc = fail("b200_model_create: model kind %d not implemented", desc->kind);
     }
     if (rc) {
@@ -179,35 +191,68 @@ extern "C" void b200_model_destroy(b200_model* m) { delete m; }
 extern "C" int b200_model_n(const b200_model* m) { return m ? m->n : -1; }
 
 // ------------------------------------------------------------------------------------------------
-// dispatch helpers
+// dispatch helpers: (model kind, n) -> (Model, NPL elements per thread, W warps per chain)
+//   n <= 256   : chain = warp  (W = 1), NPL in {1,2,4,6,8}
+//   n <= 4096  : chain = CTA of 8 warps (W = 8), NPL in {2,4,8,12,16}   (models that implement the team path)
 // ------------------------------------------------------------------------------------------------
-static int npl_for(int n) {
+static constexpr int kTeamW = 8;
+static int npl_warp(int n) {
     const int need = (n + 31) / 32;
     const int opts[] = {1, 2, 4, 6, 8};
     for (int o : opts)
         if (need <= o) return o;
     return 0;
 }
+static int npl_team(int n) {
+    const int need = (n + 32 * kTeamW - 1) / (32 * kTeamW);
+    const int opts[] = {2, 4, 8, 12, 16};
+    for (int o : opts)
+        if (need <= o) return o;
+    return 0;
+}
+static bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
 
-// Calls f.template operator()<Model, NPL>(params) for the model's kind and size.
+// Calls f.template operator()<Model, NPL, W>(params) for the model's kind and size.
 template <class F>
 static int dispatch(const b200_model* m, F&& f) {
-    const int npl = npl_for(m->n);
-    if (!npl) return fail("n=%d exceeds the warp-team limit (256); block-team kernels not built for this model", m->n);
-#define B200_CASE_NPL(MODEL, PARAMS)                                          \
-    switch (npl) {                                                            \
-        case 1: return f.template operator()<MODEL, 1>(PARAMS);               \
-        case 2: return f.template operator()<MODEL, 2>(PARAMS);               \
-        case 4: return f.template operator()<MODEL, 4>(PARAMS);               \
-        case 6: return f.template operator()<MODEL, 6>(PARAMS);               \
-        default: return f.template operator()<MODEL, 8>(PARAMS);              \
+#define B200_WARP(MODEL, PARAMS)                                                  \
+    switch (npl_warp(m->n)) {                                                     \
+        case 1: return f.template operator()<MODEL, 1, 1>(PARAMS);                \
+        case 2: return f.template operator()<MODEL, 2, 1>(PARAMS);                \
+        case 4: return f.template operator()<MODEL, 4, 1>(PARAMS);                \
+        case 6: return f.template operator()<MODEL, 6, 1>(PARAMS);                \
+        case 8: return f.template operator()<MODEL, 8, 1>(PARAMS);                \
+        default: break;                                                           \
+    }
+#define B200_TEAM(MODEL, PARAMS)                                                  \
+    switch (npl_team(m->n)) {                                                     \
+        case 2: return f.template operator()<MODEL, 2, kTeamW>(PARAMS);           \
+        case 4: return f.template operator()<MODEL, 4, kTeamW>(PARAMS);           \
+        case 8: return f.template operator()<MODEL, 8, kTeamW>(PARAMS);           \
+        case 12: return f.template operator()<MODEL, 12, kTeamW>(PARAMS);         \
+        case 16: return f.template operator()<MODEL, 16, kTeamW>(PARAMS);         \
+        default: break;                                                           \
     }
     switch (m->kind) {
-        case B200_MODEL_STD_NORMAL: B200_CASE_NPL(StdNormalModel, m->std_normal)
-        case B200_MODEL_EIGHT_SCHOOLS: B200_CASE_NPL(EightSchoolsModel, m->eight)
-        case B200_MODEL_RADON: B200_CASE_NPL(RadonModel, m->radon)
+        case B200_MODEL_STD_NORMAL:
+            if (m->n <= 256 && !env_flag("B200_FORCE_TEAM")) { B200_WARP(StdNormalModel, m->std_normal) }
+            B200_TEAM(StdNormalModel, m->std_normal)
+            return fail("std_normal: n=%d exceeds 4096", m->n);
+        case B200_MODEL_EIGHT_SCHOOLS:
+            B200_WARP(EightSchoolsModel, m->eight)
+            return fail("eight_schools: n=%d exceeds the chain-per-warp limit (256)", m->n);
+        case B200_MODEL_RADON:
+            B200_WARP(RadonModel, m->radon)
+            return fail("radon: n=%d exceeds the chain-per-warp limit (256)", m->n);
+        case B200_MODEL_STOCHVOL:
+            B200_TEAM(StochVolModel, m->stochvol)
+            return fail("stochvol: n=%d exceeds 4096", m->n);
     }
-#undef B200_CASE_NPL
+#undef B200_WARP
+#undef B200_TEAM
     return fail("dispatch: model kind %d not implemented", m->kind);
 }
 
@@ -268,15 +313,15 @@ static int env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 struct LogpLaunch {
     const b200_model* m; int C; const double* q; double* logp; double* grad; cudaStream_t st;
-    template <class Model, int NPL>
+    template <class Model, int NPL, int W>
     int operator()(const typename Model::Params& MP) const {
-        const int wpb = 8;
+        const int wpb = (W == 1) ? 8 : 1;  // chains per CTA
         const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
-        const size_t smem = data + (size_t)wpb * 2 * 32 * NPL * sizeof(double);
-        auto kern = logp_grad_warp_kernel<Model, NPL>;
+        const size_t smem = data + (size_t)wpb * (2 * 32 * W * NPL + (W > 1 ? 8 * W : 0)) * sizeof(double);
+        auto kern = logp_grad_warp_kernel<Model, NPL, W>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
-        kern<<<blocks, wpb * 32, smem, st>>>(MP, m->n, C, q, logp, grad);
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MP, m->n, C, q, logp, grad);
         CU(cudaGetLastError());
         return 0;
     }
@@ -308,15 +353,15 @@ extern "C" int b200_logp_dlogp(b200_model* m, const double* q, int32_t C, double
 struct LeapLaunch {
     const b200_model* m; int C, n_steps; const double *var, *eps; double *q, *p, *v, *grad, *energy, *logp;
     long long* idx; cudaStream_t st;
-    template <class Model, int NPL>
+    template <class Model, int NPL, int W>
     int operator()(const typename Model::Params& MP) const {
-        const int wpb = 8;
+        const int wpb = (W == 1) ? 8 : 1;
         const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
-        const size_t smem = data + (size_t)wpb * 2 * 32 * NPL * sizeof(double);
-        auto kern = leapfrog_warp_kernel<Model, NPL>;
+        const size_t smem = data + (size_t)wpb * (2 * 32 * W * NPL + (W > 1 ? 8 * W : 0)) * sizeof(double);
+        auto kern = leapfrog_warp_kernel<Model, NPL, W>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
-        kern<<<blocks, wpb * 32, smem, st>>>(MP, m->n, C, var, eps, n_steps, q, p, v, grad, energy, logp, idx);
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MP, m->n, C, var, eps, n_steps, q, p, v, grad, energy, logp, idx);
         CU(cudaGetLastError());
         return 0;
     }
@@ -357,18 +402,19 @@ extern "C" int b200_leapfrog(b200_model* m, const double* var, const double* eps
 // ------------------------------------------------------------------------------------------------
 struct NutsLaunch {
     const b200_model* m; NutsDev P; cudaStream_t st;
-    template <class Model, int NPL>
+    template <class Model, int NPL, int W>
     int operator()(const typename Model::Params& MP) {
-        constexpr int NP = 32 * NPL;
-        int wpb = env_int("B200_NUTS_WPB", 4);
-        int hot = env_int("B200_NUTS_HOT", 2);
+        constexpr int NP = 32 * W * NPL;
+        constexpr bool SUBS = (W > 1) ? true : (B200_SUBTREE_SMEM != 0);
+        int wpb = (W == 1) ? env_int("B200_NUTS_WPB", 4) : 1;  // chains per CTA
+        int hot = env_int("B200_NUTS_HOT", (W == 1) ? 2 : 1);
         wpb = std::max(1, std::min(wpb, B200_NUTS_THREADS / 32));
         hot = std::max(0, std::min(hot, P.max_td));
         const size_t data = (Model::shared_bytes(MP) + 15) & ~(size_t)15;
-        size_t smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot);
+        size_t smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot, SUBS, W);
         while (smem > 227 * 1024 && hot > 0) {  // shrink the hot window until the CTA fits
             --hot;
-            smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot);
+            smem = data + (size_t)wpb * nuts_warp_smem_bytes(NP, hot, SUBS, W);
         }
         if (smem > 227 * 1024) return fail("nuts: shared memory request %zu B exceeds 227 KB", smem);
         P.hot_levels = hot;
@@ -376,11 +422,11 @@ struct NutsLaunch {
         P.scratch_stride = nuts_scratch_doubles(NP, P.max_td);
         CU(scratch.alloc((size_t)P.C * P.scratch_stride * sizeof(double)));
         P.scratch = scratch.as<double>();
-        auto kern = nuts_warp_kernel<Model, NPL>;
+        auto kern = nuts_warp_kernel<Model, NPL, W, SUBS>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = (P.C + wpb - 1) / wpb;
         Timer t(st);
-        kern<<<blocks, wpb * 32, smem, st>>>(P, MP);
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(P, MP);
         CU(cudaGetLastError());
         t.stop(1);
         CU(cudaStreamSynchronize(st));

@@ -107,6 +107,47 @@ __device__ __forceinline__ void warp_sum_bcast_n(double (&x)[N], int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Team = the W warps that own one chain (W = 1: a warp, several chains per CTA; W > 1: the whole CTA).
+// Thread t of the team owns elements t, t + 32W, ...  Cross-warp reductions go through `red`
+// (W x 8 doubles of shared memory) in a fixed order, so all threads of the team get identical bits.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void team_sync() {
+    if constexpr (W == 1) __syncwarp(); else __syncthreads();
+}
+
+template <int W, int N>
+__device__ __forceinline__ void team_sum_n(double (&x)[N], int tid, double* red) {
+    static_assert(N <= 8, "team_sum_n handles up to 8 values");
+    if constexpr (W == 1) {
+        if constexpr (N >= 4) warp_sum_bcast_n(x, tid); else warp_sum_n(x);
+    } else {
+        warp_sum_n(x);
+        const int w = tid >> 5;
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) red[w * 8 + i] = x[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double a = red[i];
+#pragma unroll
+            for (int ww = 1; ww < W; ++ww) a += red[ww * 8 + i];
+            x[i] = a;
+        }
+        __syncthreads();
+    }
+}
+
+template <int W>
+__device__ __forceinline__ double team_sum(double x, int tid, double* red) {
+    double a[1] = {x};
+    team_sum_n<W>(a, tid, red);
+    return a[0];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bulk TMA (cp.async.bulk, SASS UBLKCP): stage a contiguous global array into shared memory,
 // completion signalled on an mbarrier.  bytes must be a multiple of 16, both addresses 16B aligned.
 // ---------------------------------------------------------------------------------------------

@@ -10,6 +10,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef B200_EVAL_INLINE
+#define B200_EVAL_INLINE  // define as __noinline__ to keep one copy of the model function (I-cache footprint)
+#endif
+
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------------
@@ -21,17 +25,17 @@ struct StdNormalModel {
     };
     __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
     __device__ static void stage(const Params&, char*, uint64_t*) {}
-    template <int NPL>
-    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane) {
+    template <int NPL, int W>
+    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int tid, double* red) {
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = tid + 32 * W * k;
             const double x = q_s[i];
             s = fma(x, x, s);
             g_s[i] = -x;
         }
-        s = warp_sum(s);
+        s = team_sum<W>(s, tid, red);
         return -0.5 * s - P.n * B200_HALF_LOG_2PI;
     }
 };
@@ -51,8 +55,9 @@ struct EightSchoolsModel {
     };
     __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
     __device__ static void stage(const Params&, char*, uint64_t*) {}
-    template <int NPL>
-    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane) {
+    template <int NPL, int W>
+    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane, double*) {
+        static_assert(W == 1, "EightSchoolsModel is a chain-per-warp model");
         const double mu = q_s[0], ltau = q_s[1];
         const double tau = exp(ltau);
         double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum r, sum r*tt, sum tt^2, sum loglik (w/o const)
@@ -118,8 +123,10 @@ struct RadonModel {
         }
     }
 
-    template <int NPL>
-    __device__ static double eval(const Params& P, const char* smem, const double* q_s, double* g_s, int lane) {
+    template <int NPL, int W>
+    __device__ B200_EVAL_INLINE static double eval(const Params& P, const char* smem, const double* q_s, double* g_s, int lane,
+                                                   double*) {
+        static_assert(W == 1, "RadonModel is a chain-per-warp model");
         const double2* xy = reinterpret_cast<const double2*>(smem) + lane;
         const int32_t* seg = reinterpret_cast<const int32_t*>(smem + xy_bytes(P));
         const int32_t* rows = seg + P.M * 32;
@@ -201,6 +208,78 @@ struct RadonModel {
         lp += -0.5 * acc[5] - J * B200_HALF_LOG_2PI;
         lp += -0.5 * acc[6] - J * B200_HALF_LOG_2PI;
         lp += -0.5 * acc[0] * inv_e2 - P.n_obs * (B200_HALF_LOG_2PI + leps);
+        return lp;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Stochastic volatility (BASELINE config 4).  q = [mu, z_phi, log sigma, h_0 .. h_{T-1}], chain = CTA.
+//   mu~Normal(0,5); phi~Uniform(-1,1) (interval transform); sigma~Exponential(10) (log transform);
+//   h~AR(rho=[phi], sigma, init_dist=Normal(0,1)); y_t~Normal(0, exp((mu+h_t)/2))
+// Densities: AR logp timeseries.py:646-676; Uniform + IntervalTransform continuous.py:309,
+// logprob/transforms.py:1026-1073; Exponential continuous.py:1478-1480; Normal :526-527.
+// Gradient: SURVEY Appendix C-4.  Thread t handles times t, t+TS, ...; neighbours h_{t-1}, h_{t+1} come
+// from the chain's shared-memory copy of q; y_t^2 is read through L1 (24 KB, shared by all CTAs of the SM).
+// ------------------------------------------------------------------------------------------------
+struct StochVolModel {
+    struct Params {
+        const double* y2;  // [T] y_t^2
+        int T;
+    };
+    __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
+    __device__ static void stage(const Params&, char*, uint64_t*) {}
+    template <int NPL, int W>
+    __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int tid, double* red) {
+        constexpr int TS = 32 * W;
+        const int T = P.T;
+        const double mu = q_s[0], zphi = q_s[1], lsig = q_s[2];
+        const double* h = q_s + 3;
+        double* gh = g_s + 3;
+        const double s = sigmoid(zphi);
+        const double phi = 2.0 * s - 1.0;
+        const double sig = exp(lsig);
+        const double inv_s2 = exp(-2.0 * lsig);
+        // acc: sum w_t, sum e_t h_{t-1}, sum e_t^2, sum h_t
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+        for (int k = 0; k < NPL; ++k) {
+            const int t = tid + TS * k;
+            if (t < T) {
+                const double ht = h[t];
+                const double w = P.y2[t] * exp(-(mu + ht));
+                double g = 0.5 * w - 0.5;
+                acc[0] += w;
+                acc[3] += ht;
+                if (t >= 1) {
+                    const double hm = h[t - 1];
+                    const double e = ht - phi * hm;
+                    g -= e * inv_s2;
+                    acc[1] = fma(e, hm, acc[1]);
+                    acc[2] = fma(e, e, acc[2]);
+                } else {
+                    g -= ht;  // init_dist Normal(0,1) on h_0
+                }
+                if (t + 1 < T) {
+                    const double en = h[t + 1] - phi * ht;
+                    g = fma(phi * inv_s2, en, g);
+                }
+                gh[t] = g;
+            }
+        }
+        team_sum_n<W>(acc, tid, red);
+        const double h0 = h[0];
+        if (tid == 0) {
+            g_s[0] = -mu * (1.0 / 25.0) + (0.5 * acc[0] - 0.5 * T);
+            g_s[1] = (1.0 - 2.0 * s) + 2.0 * s * (1.0 - s) * acc[1] * inv_s2;
+            g_s[2] = 1.0 - 10.0 * sig + acc[2] * inv_s2 - (double)(T - 1);
+        }
+        const double z = mu * 0.2;
+        double lp = -0.5 * z * z - B200_HALF_LOG_2PI - 1.6094379124341002818;           // Normal(mu | 0, 5)
+        lp += -2.0 * softplus(-zphi) - zphi;                                              // Uniform(-1,1) + interval Jacobian
+        lp += 2.3025850929940456840 - 10.0 * sig + lsig;                                  // Exponential(10) + log Jacobian
+        lp += -0.5 * h0 * h0 - B200_HALF_LOG_2PI;                                         // h_0 ~ Normal(0,1)
+        lp += -0.5 * acc[2] * inv_s2 - (T - 1) * (B200_HALF_LOG_2PI + lsig);              // innovations
+        lp += -0.5 * acc[0] - T * B200_HALF_LOG_2PI - 0.5 * (T * mu + acc[3]);            // observations
         return lp;
     }
 };

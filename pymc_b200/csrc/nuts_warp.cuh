@@ -59,9 +59,10 @@ __host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
 #ifndef B200_SUBTREE_SMEM
 #define B200_SUBTREE_SMEM 0  // 1: left.p / p_sum / proposal q of the subtree under construction live in shared memory
 #endif                       //    (frees 6*NPL registers per lane -> more resident warps); 0: in registers
-__host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot) {
-    const int vecs = 2 + (B200_SUBTREE_SMEM ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
-    return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double);
+// (per chain; + 3 vectors when the subtree under construction is kept in shared memory; + the team's reduction pad)
+__host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool subs = B200_SUBTREE_SMEM, int W = 1) {
+    const int vecs = 2 + (subs ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
+    return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double) + (W > 1 ? W * 8 * sizeof(double) : 0);
 }
 
 #ifndef B200_NUTS_THREADS
@@ -70,9 +71,12 @@ __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot) {
 #ifndef B200_NUTS_MINBLOCKS
 #define B200_NUTS_MINBLOCKS 1  // __launch_bounds__ min CTAs/SM: the register budget knob
 #endif
-template <class Model, int NPL>
-__global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
-    constexpr int NP = 32 * NPL;
+// W = warps per chain (team).  SUBS = subtree-under-construction vectors in shared memory instead of registers.
+template <class Model, int NPL, int W, bool SUBS>
+__global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 : B200_NUTS_MINBLOCKS)
+    nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
+    constexpr int TS = 32 * W;      // threads per chain
+    constexpr int NP = TS * NPL;    // padded vector length
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
 
@@ -86,33 +90,30 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     }
     const char* data_s = smem_raw;
 
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // `lane` is the thread's index inside its team (0 .. TS-1)
+    const int lane = (W == 1) ? (threadIdx.x & 31) : (int)threadIdx.x;
+    const int wib = (W == 1) ? (threadIdx.x >> 5) : 0, wpb = (W == 1) ? (blockDim.x >> 5) : 1;
     const int chain = blockIdx.x * wpb + wib;
-    if (chain >= P.C) return;  // no CTA-wide barrier after this point
+    if (chain >= P.C) return;  // no CTA-wide barrier after this point (W == 1); W > 1: the whole CTA leaves
 
     const int hot = P.hot_levels;
-    double* ws = reinterpret_cast<double*>(smem_raw + data_bytes + wib * nuts_warp_smem_bytes(NP, hot));
+    double* ws = reinterpret_cast<double*>(smem_raw + data_bytes + wib * nuts_warp_smem_bytes(NP, hot, SUBS, W));
     double* q_s = ws;
     double* g_s = ws + NP;
-#if B200_SUBTREE_SMEM
-    double* lp_s = ws + 2 * NP + lane;
-    double* ps_s = ws + 3 * NP + lane;
-    double* pq_s = ws + 4 * NP + lane;
-    double* hot_base = ws + 5 * NP;
-#define LP(k) lp_s[32 * (k)]
-#define PS(k) ps_s[32 * (k)]
-#define PQ(k) pq_s[32 * (k)]
-#else
-    double* hot_base = ws + 2 * NP;
-    double lp_r[NPL], ps_r[NPL], pq_r[NPL];
-#define LP(k) lp_r[k]
-#define PS(k) ps_r[k]
-#define PQ(k) pq_r[k]
-#endif
+    double* sub_s = ws + 2 * NP + lane;            // SUBS: left.p, p_sum, proposal q of the subtree under construction
+    double* hot_base = ws + (SUBS ? 5 : 2) * NP;
+    double lp_r[SUBS ? 1 : NPL], ps_r[SUBS ? 1 : NPL], pq_r[SUBS ? 1 : NPL];
+    auto LPf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[TS * k]; else return lp_r[k]; };
+    auto PSf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[NP + TS * k]; else return ps_r[k]; };
+    auto PQf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[2 * NP + TS * k]; else return pq_r[k]; };
+#define LP(k) LPf(k)
+#define PS(k) PSf(k)
+#define PQ(k) PQf(k)
     double* sc_logw = hot_base + (hot > 0 ? 2 + 4 * (hot - 1) : 0) * NP;
     double* sc_pe = sc_logw + kMaxLevels;
     double* sc_plogp = sc_pe + kMaxLevels;
     double* sc_pidx = sc_plogp + kMaxLevels;
+    double* red = sc_pidx + kMaxLevels;  // W x 8 doubles, cross-warp reductions (W > 1)
     double* gs = P.scratch + (long long)chain * P.scratch_stride;
 
     // which: 0 = left.p, 1 = right.p, 2 = p_sum, 3 = proposal q.  Level 0 (a single leaf) keeps only 2, 3.
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     double var[NPL], p[NPL];
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
-        const int i = lane + 32 * k;
+        const int i = lane + TS * k;
         q_s[i] = (i < n) ? P.q0[(long long)chain * n + i] : 0.0;
         g_s[i] = 0.0;
         var[k] = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     }
     long long n_grad = 0;
     int bad_at = -1;
-    __syncwarp();
+    team_sync<W>();
 
     for (int it = 0; it < Ttot; ++it) {
         const bool tuning = it < P.tune;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
         // ---- p0 = potential.random(): inv_std * z  (quadpotential.py:323-326, :617-619) ------------
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             double zz = 0.0;
             if (i < n) {
                 zz = (P.momentum_source == B200_MOMENTUM_HOST_BUFFER)
@@ -178,14 +179,14 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
             p[k] = (1.0 / sqrt(var[k])) * zz;
         }
         // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
-        __syncwarp();
-        const double logp0 = Model::template eval<NPL>(M, data_s, q_s, g_s, lane);
-        __syncwarp();
+        team_sync<W>();
+        const double logp0 = Model::template eval<NPL, W>(M, data_s, q_s, g_s, lane, red);
+        team_sync<W>();
         ++n_grad;
         double kin = 0.0;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) kin = fma(p[k], var[k] * p[k], kin);
-        const double E0 = 0.5 * warp_sum(kin) - logp0;
+        const double E0 = 0.5 * team_sum<W>(kin, lane, red) - logp0;
         if (!isfinite(E0)) {  // "Bad initial energy" (base_hmc.py:205-224): freeze the chain
             bad_at = it;
             break;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
         double* PSv = gvec(G_PS); double* PQv = gvec(G_PQ); double* NEARP = gvec(G_NEARP);
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             const double qi = q_s[i], gi = g_s[i];
             Lq[i] = qi; Rq[i] = qi; PQv[i] = qi;
             Lg[i] = gi; Rg[i] = gi;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
             int w_idx = dir > 0 ? R_idx : L_idx;
 #pragma unroll
             for (int k = 0; k < NPL; ++k) {
-                const int i = lane + 32 * k;
+                const int i = lane + TS * k;
                 q_s[i] = Eq[i];
                 g_s[i] = Eg[i];
                 p[k] = Ep[i];
@@ -239,22 +240,22 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 // -- one leapfrog (integration.py:109-145)
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     p[k] = fma(dt, g_s[i], p[k]);
                     q_s[i] = fma(es, var[k] * p[k], q_s[i]);
                 }
-                __syncwarp();
-                const double logp = Model::template eval<NPL>(M, data_s, q_s, g_s, lane);
-                __syncwarp();
+                team_sync<W>();
+                const double logp = Model::template eval<NPL, W>(M, data_s, q_s, g_s, lane, red);
+                team_sync<W>();
                 ++n_grad;
                 double kk = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     p[k] = fma(dt, g_s[i], p[k]);
                     kk = fma(p[k], var[k] * p[k], kk);
                 }
-                const double E = 0.5 * warp_sum(kk) - logp;
+                const double E = 0.5 * team_sum<W>(kk, lane, red) - logp;
                 w_idx += dir;
                 // -- _single_step bookkeeping (nuts.py:406-440)
                 ++n_prop;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 for (int k = 0; k < NPL; ++k) {
                     LP(k) = p[k];
                     PS(k) = p[k];
-                    PQ(k) = q_s[lane + 32 * k];
+                    PQ(k) = q_s[lane + TS * k];
                 }
                 c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
 
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                     if (h == 0) {
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + 32 * k;
+                            const int i = lane + TS * k;
                             const double tp = t_ps[i];
                             const double s = tp + PS(k);
                             dots[0] = fma(s, var[k] * tp, dots[0]);
@@ -294,13 +295,13 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                             PS(k) = s;
                         }
                         double d2[2] = {dots[0], dots[1]};
-                        warp_sum_n(d2);
+                        team_sum_n<W>(d2, lane, red);
                         dots[0] = d2[0]; dots[1] = d2[1];
                         dots[2] = dots[3] = dots[4] = dots[5] = 1.0;
                     } else {
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + 32 * k;
+                            const int i = lane + TS * k;
                             const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
                             const double s = tp + PS(k);
                             const double vl = var[k] * tl, vr = var[k] * p[k];
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                             PS(k) = s;
                         }
                     }
-                    if (h) warp_sum_bcast_n(dots, lane);
+                    if (h) team_sum_n<W>(dots, lane, red);
                     const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
                                       (dots[4] <= 0) || (dots[5] <= 0);
                     // logw = logaddexp(t, c) = max + log1p(e), e = exp(-|c - t|); the pick  log(u) < c - logw  is
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                     if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                         const double* t_pq = lvl(h, 3);
 #pragma unroll
-                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + 32 * k];
+                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + TS * k];
                         c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
                     }
                     c_logw = logw;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                     if (h == 0) {
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + 32 * k;
+                            const int i = lane + TS * k;
                             s_ps[i] = PS(k);
                             s_pq[i] = PQ(k);
                         }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                         double* s_rp = lvl(h, 1);
 #pragma unroll
                         for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + 32 * k;
+                            const int i = lane + TS * k;
                             s_lp[i] = LP(k);
                             s_rp[i] = p[k];
                             s_ps[i] = PS(k);
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                     if (lane == 0) {
                         sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
                     }
-                    __syncwarp();
+                    team_sync<W>();
                 }
             }
             ++depth;  // nuts.py:365 (counts the aborted doubling too)
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 double* Ng = dir > 0 ? Rg : Lg;
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     Nq[i] = q_s[i];
                     Ng[i] = g_s[i];
                     Np[i] = p[k];
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 const double e_w = exp(-fabs(dlw));
                 if (dlw >= 0.0 || u < e_w) {  // log(u) < c_logw - m_logw
 #pragma unroll
-                    for (int k = 0; k < NPL; ++k) PQv[lane + 32 * k] = PQ(k);
+                    for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = PQ(k);
                     m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
                 }
                 m_logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     const double so = PSv[i], fp = FARP[i], np_ = NEARP[i];
                     const double s = so + PS(k);
                     PSv[i] = s;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                     dots[4] = fma(b, var[k] * np_, dots[4]);
                     dots[5] = fma(b, vw, dots[5]);
                 }
-                warp_sum_bcast_n(dots, lane);
+                team_sum_n<W>(dots, lane, red);
                 if ((dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) || (dots[4] <= 0) ||
                     (dots[5] <= 0)) {
                     turned = true;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
         const int t_out = P.store_warmup ? it : it - P.tune;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             const double qi = PQv[i];
             q_s[i] = qi;
             PQ(k) = qi;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 double* bm = gvec(bg_m); double* bv = gvec(bg_v);
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     const double x = PQ(k);
                     double mean = fm[i];
                     double d0 = x - mean;
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 const double* fv = gvec(fg_v);
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     if (i < n) var[k] = fmin(fmax(fv[i] / fg_n, 1e-12), 1e12);
                 }
             }
@@ -491,8 +492,8 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
                 double* bm = gvec(bg_m); double* bv = gvec(bg_v);
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    bm[lane + 32 * k] = 0.0;
-                    bv[lane + 32 * k] = 0.0;
+                    bm[lane + TS * k] = 0.0;
+                    bv[lane + TS * k] = 0.0;
                 }
             }
             ++k_samples;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
             if (P.st.model_logp) P.st.model_logp[o] = m_plogp;
         }
         (void)turned;
-        __syncwarp();
+        team_sync<W>();
     }
 
     // ---- end of run: hand the streams and adaptation results back --------------------------------------
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
     if (P.sm.final_var) {
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             if (i < n) P.sm.final_var[(long long)chain * n + i] = var[k];
         }
     }
@@ -540,12 +541,13 @@ __global__ void __launch_bounds__(B200_NUTS_THREADS, B200_NUTS_MINBLOCKS) nuts_w
 // Batched logp + gradient: one warp per point.  Replaces ValueGradFunction._pytensor_function
 // (model/core.py:232-267) evaluated at C points.
 // ---------------------------------------------------------------------------------------------------
-template <class Model, int NPL>
+template <class Model, int NPL, int W>
 __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Model::Params M, int n, int C,
                                                              const double* __restrict__ q,
                                                              double* __restrict__ logp_out,
                                                              double* __restrict__ grad_out) {
-    constexpr int NP = 32 * NPL;
+    constexpr int TS = 32 * W;
+    constexpr int NP = TS * NPL;
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
     const size_t data_bytes = (Model::shared_bytes(M) + 15) & ~(size_t)15;
@@ -555,26 +557,28 @@ __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Mode
         Model::stage(M, smem_raw, &tma_bar);
         mbar_wait(&tma_bar, 0);
     }
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * 2 * NP;
+    const int lane = (W == 1) ? (threadIdx.x & 31) : (int)threadIdx.x;
+    const int wib = (W == 1) ? (threadIdx.x >> 5) : 0, wpb = (W == 1) ? (blockDim.x >> 5) : 1;
+    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * (2 * NP + (W > 1 ? 8 * W : 0));
     double* g_s = q_s + NP;
+    double* red = g_s + NP;
     for (int c = blockIdx.x * wpb + wib; c < C; c += gridDim.x * wpb) {
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             q_s[i] = (i < n) ? q[(long long)c * n + i] : 0.0;
             g_s[i] = 0.0;
         }
-        __syncwarp();
-        const double lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
-        __syncwarp();
+        team_sync<W>();
+        const double lp = Model::template eval<NPL, W>(M, smem_raw, q_s, g_s, lane, red);
+        team_sync<W>();
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             if (i < n) grad_out[(long long)c * n + i] = g_s[i];
         }
         if (lane == 0) logp_out[c] = lp;
-        __syncwarp();
+        team_sync<W>();
     }
 }
 
@@ -582,12 +586,13 @@ __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Mode
 // Batched leapfrog with a diagonal potential: compute_state (n_steps == 0) or n_steps x _step
 // (integration.py:68-75, :109-145).  One warp per chain; State is struct-of-arrays in global memory.
 // ---------------------------------------------------------------------------------------------------
-template <class Model, int NPL>
+template <class Model, int NPL, int W>
 __global__ void __launch_bounds__(256)
     leapfrog_warp_kernel(const typename Model::Params M, int n, int C, const double* __restrict__ var_in,
                          const double* __restrict__ eps_in, int n_steps, double* q, double* p_io, double* v_io,
                          double* grad, double* energy, double* logp_io, long long* idx) {
-    constexpr int NP = 32 * NPL;
+    constexpr int TS = 32 * W;
+    constexpr int NP = TS * NPL;
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
     const size_t data_bytes = (Model::shared_bytes(M) + 15) & ~(size_t)15;
@@ -597,54 +602,56 @@ __global__ void __launch_bounds__(256)
         Model::stage(M, smem_raw, &tma_bar);
         mbar_wait(&tma_bar, 0);
     }
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * 2 * NP;
+    const int lane = (W == 1) ? (threadIdx.x & 31) : (int)threadIdx.x;
+    const int wib = (W == 1) ? (threadIdx.x >> 5) : 0, wpb = (W == 1) ? (blockDim.x >> 5) : 1;
+    double* q_s = reinterpret_cast<double*>(smem_raw + data_bytes) + (size_t)wib * (2 * NP + (W > 1 ? 8 * W : 0));
     double* g_s = q_s + NP;
+    double* red = g_s + NP;
     for (int c = blockIdx.x * wpb + wib; c < C; c += gridDim.x * wpb) {
         double var[NPL], p[NPL];
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             const bool in = i < n;
             q_s[i] = in ? q[(long long)c * n + i] : 0.0;
             g_s[i] = (in && n_steps > 0) ? grad[(long long)c * n + i] : 0.0;
             p[k] = in ? p_io[(long long)c * n + i] : 0.0;
             var[k] = in ? var_in[(long long)c * n + i] : 1.0;
         }
-        __syncwarp();
+        team_sync<W>();
         double lp = 0.0, E = 0.0;
         if (n_steps == 0) {
-            lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
-            __syncwarp();
+            lp = Model::template eval<NPL, W>(M, smem_raw, q_s, g_s, lane, red);
+            team_sync<W>();
             double kk = 0.0;
 #pragma unroll
             for (int k = 0; k < NPL; ++k) kk = fma(p[k], var[k] * p[k], kk);
-            E = 0.5 * warp_sum(kk) - lp;
+            E = 0.5 * team_sum<W>(kk, lane, red) - lp;
         } else {
             const double es = eps_in[c], dt = 0.5 * es;
             for (int s = 0; s < n_steps; ++s) {
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + 32 * k;
+                    const int i = lane + TS * k;
                     p[k] = fma(dt, g_s[i], p[k]);
                     q_s[i] = fma(es, var[k] * p[k], q_s[i]);
                 }
-                __syncwarp();
-                lp = Model::template eval<NPL>(M, smem_raw, q_s, g_s, lane);
-                __syncwarp();
+                team_sync<W>();
+                lp = Model::template eval<NPL, W>(M, smem_raw, q_s, g_s, lane, red);
+                team_sync<W>();
                 double kk = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    p[k] = fma(dt, g_s[lane + 32 * k], p[k]);
+                    p[k] = fma(dt, g_s[lane + TS * k], p[k]);
                     kk = fma(p[k], var[k] * p[k], kk);
                 }
-                E = 0.5 * warp_sum(kk) - lp;
+                E = 0.5 * team_sum<W>(kk, lane, red) - lp;
             }
             if (lane == 0) idx[c] += (es > 0 ? 1 : (es < 0 ? -1 : 0)) * (long long)n_steps;
         }
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
-            const int i = lane + 32 * k;
+            const int i = lane + TS * k;
             if (i < n) {
                 const long long o = (long long)c * n + i;
                 q[o] = q_s[i];
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(256)
             energy[c] = E;
             logp_io[c] = lp;
         }
-        __syncwarp();
+        team_sync<W>();
     }
 }
 

@@ -12,6 +12,10 @@ SPEC_OF = {
     "radon_adapt": models.radon,
     "radon_warm_adapt": models.radon,
     "radon_small_adapt": lambda: models.radon(40, 7, 5),
+    "std_normal_team_fixed": lambda: models.std_normal(300),
+    "stochvol_small_adapt": lambda: models.stochvol(T=100, seed=4),
+    "stochvol_small_fixed": lambda: models.stochvol(T=100, seed=4),
+    "stochvol_fixed": models.stochvol,
 }
 TREE_KW = {"radon_small_adapt": dict(max_treedepth=6, early_max_treedepth=4)}
 DISCRETE = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_max_treedepth"]

@@ -28,7 +28,8 @@ def compiled():
     return get
 
 
-MODELS = ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "radon_small_adapt"]
+MODELS = ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "radon_small_adapt",
+          "std_normal_team_fixed", "stochvol_small_fixed", "stochvol_fixed"]  # last three: chain-per-CTA kernels
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -39,7 +40,8 @@ def test_logp_grad_matches_oracle(compiled, name):
     spec = cm.spec
     f = logp_numpy.make_logp(spec)
     rng = np.random.default_rng(0)
-    Q = spec.initial_point() + rng.uniform(-2.0, 2.0, (257, spec.n))  # ragged vs the 8-warp CTA
+    nq, amp = (257, 2.0) if spec.n < 1000 else (19, 0.5)
+    Q = spec.initial_point() + rng.uniform(-amp, amp, (nq, spec.n))  # ragged vs the 8-warp CTA
     lp, g = cm.logp_dlogp(Q)
     lo = np.array([f(q)[0] for q in Q])
     go = np.array([f(q)[1] for q in Q])
@@ -77,7 +79,7 @@ def test_leapfrog_reversible(compiled, eps, n_steps):
     np.testing.assert_allclose(b["energy"], s["energy"], rtol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["eight_schools_fixed", "radon_fixed"])
+@pytest.mark.parametrize("name", ["eight_schools_fixed", "radon_fixed", "stochvol_small_fixed"])
 def test_leapfrog_matches_oracle(compiled, name):
     from oracle import logp_numpy, nuts_numpy
 
@@ -101,7 +103,8 @@ def test_leapfrog_matches_oracle(compiled, name):
         assert out["idx"][c] == s.idx
 
 
-@pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed"])
+@pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "std_normal_team_fixed",
+                                  "stochvol_small_fixed", "stochvol_fixed"])
 def test_nuts_fixed_step_identical_draws(compiled, golden, name):
     """Same stream seeds, same fixed step size and mass matrix => same accepted draws as the reference."""
     d = golden(name)
@@ -128,7 +131,7 @@ def test_stream_consumption_order(compiled, golden, name):
     assert np.array_equal(states.view(np.uint64), want.view(np.uint64))
 
 
-@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_adapt", "radon_small_adapt"])
+@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_adapt", "radon_small_adapt", "stochvol_small_adapt"])
 def test_nuts_single_draw_replay_of_adaptive_run(compiled, golden, name):
     """Every draw of a full adaptive reference run (huge early step sizes, divergences, depth caps) replayed
     from its golden pre-draw state."""

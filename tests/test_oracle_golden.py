@@ -22,7 +22,8 @@ def _gen_from_state(state_u64x4):
     return g
 
 
-@pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed"])
+@pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "std_normal_team_fixed",
+                                  "stochvol_small_fixed", "stochvol_fixed"])
 def test_fixed_step_chains_reproduce_golden(golden, name):
     d = golden(name)
     spec = SPEC_OF[name]()
@@ -38,7 +39,7 @@ def test_fixed_step_chains_reproduce_golden(golden, name):
         assert np.max(np.abs(st["energy"] - d["stat_energy"][c])) <= 1e-9
 
 
-@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_small_adapt", "radon_adapt"])
+@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_small_adapt", "radon_adapt", "stochvol_small_adapt"])
 def test_single_draw_replay_of_adaptive_golden(golden, name):
     d = golden(name)
     spec = SPEC_OF[name]()

@@ -73,6 +73,8 @@ typedef struct b200_model_desc {
     const int32_t* idx;  /* RADON: county_idx[n_obs] in [0, n_groups)                                 */
     const uint8_t* y_u8; /* LOGISTIC: y[n_obs] in {0,1}                                               */
     double scalar0;      /* MVGAUSS: sum(log diag L) (constant of the log-density)                    */
+    const double* m1;    /* MVGAUSS: L^-T [n][n] row-major (p0 = solve_triangular(L^T, z) = L^-T z)   */
+    const double* m2;    /* MVGAUSS: Cholesky factor L [n][n] row-major (v0 = Sigma p0 = L z)         */
 } b200_model_desc;
 
 /* NumPy PCG64 stream state (numpy.random.PCG64().state["state"]): 128-bit LCG state and increment.

@@ -26,13 +26,16 @@ STAT_KEYS = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_
              "step_size_bar", "mean_tree_accept", "energy", "energy_error", "max_energy_error", "model_logp"]
 
 
-def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None, init_var=None):
+def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None, init_var=None,
+                  dense=False):
     """One chain through the verbatim reference.  adapt=True: DiagAdapt(mean=q0, ones, weight 10) + dual
     averaging (what init_nuts builds, mcmc.py:1890-1894); adapt=False: fixed QuadPotentialDiag(var), fixed eps."""
     f = logp_numpy.make_logp(spec)
     qp = ref_loader.quadpotential()
     n = spec.n
-    if adapt:
+    if dense:  # QuadPotentialFull with the model's covariance (quadpotential.py:680-725); `adapt` = step size only
+        pot = qp.QuadPotentialFull(spec.data["cov"])
+    elif adapt:
         pot = qp.QuadPotentialDiagAdapt(n, q0.copy(), np.ones(n) if init_var is None else np.array(init_var, dtype="d"), 10)
     else:
         pot = qp.QuadPotentialDiag(np.ones(n) if var is None else np.asarray(var, dtype="d"))
@@ -52,13 +55,13 @@ def run_reference(spec, q0, *, seed, tune, draws, adapt, var=None, eps=None, nut
         # what a single-draw replay ("teacher forcing") needs: stream position, mass matrix, step size
         s = step.rng.bit_generator.state["state"]
         pre_rng.append([s["state"] >> 64, s["state"] & (2**64 - 1), s["inc"] >> 64, s["inc"] & (2**64 - 1)])
-        pre_var.append(np.array(step.potential._var if adapt else step.potential.v))
+        pre_var.append(np.zeros(1) if dense else np.array(step.potential._var if adapt else step.potential.v))
         pt, st = step.step(pt)
         used_eps.append(float(step.step_size))  # set inside astep: the eps this draw integrated with
         qs.append(np.concatenate([np.ravel(pt[v.name]) for v in spec.vars]))
         sts.append(st[0])
     stats = {k: np.array([s[k] for s in sts]) for k in STAT_KEYS}
-    final_var = np.array(step.potential._var if adapt else step.potential.v)
+    final_var = np.zeros(1) if dense else np.array(step.potential._var if adapt else step.potential.v)
     extra = dict(pre_rng=np.array(pre_rng, dtype=np.uint64), pre_var=np.array(pre_var), used_eps=np.array(used_eps))
     return np.array(qs), stats, final_var, float(step.step_size), extra
 
@@ -71,7 +74,7 @@ def noise(seed, T, n):
 
 
 def case(name, spec_name, spec_args, q0s, seeds, *, tune, draws, adapt, var=None, eps=None, nuts_kwargs=None,
-         init_var=None):
+         init_var=None, dense=False):
     spec = models.BUILDERS[spec_name](**spec_args)
     C = len(seeds)
     Q, ST, FV, FE, Z, EX = [], [], [], [], [], []
@@ -80,10 +83,10 @@ def case(name, spec_name, spec_args, q0s, seeds, *, tune, draws, adapt, var=None
         e = None if eps is None else float(eps[c])
         q, st, fv, fe, ex = run_reference(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, adapt=adapt, var=v,
                                           eps=e, nuts_kwargs=nuts_kwargs,
-                                          init_var=None if init_var is None else init_var[c])
+                                          init_var=None if init_var is None else init_var[c], dense=dense)
         Q.append(q); ST.append(st); FV.append(fv); FE.append(fe); EX.append(ex)
         Z.append(noise(seeds[c], tune + draws, spec.n))
-    out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, adapt=adapt, draws_q=np.array(Q),
+    out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, adapt=adapt, dense=dense, draws_q=np.array(Q),
                z=np.array(Z), final_var=np.array(FV), final_step_size=np.array(FE),
                var=np.array(var) if var is not None else np.ones((C, spec.n)),
                eps=np.array(eps) if eps is not None else np.full(C, np.nan),
@@ -154,7 +157,25 @@ def team_cases():
          eps=np.array([b[3]]))
 
 
+def lockstep_cases():
+    """Cases for the lock-step (GEMM-shaped) engine: dense mass Gaussian and logistic GLM."""
+    rng = np.random.default_rng(31)
+    mv = models.mvgauss(n=60, seed=5)
+    q0s = [rng.standard_normal(60) for _ in range(2)]
+    case("mvgauss_dense_fixed", "mvgauss", {"n": 60, "seed": 5}, q0s, [801, 802], tune=0, draws=30, adapt=False, dense=True)
+    case("mvgauss_dense_stepadapt", "mvgauss", {"n": 60, "seed": 5}, q0s[:1], [803], tune=150, draws=30, adapt=True, dense=True)
+    lg = models.logistic(n_rows=400, n_features=8, seed=3)
+    q0s = [lg.initial_point() + rng.uniform(-1, 1, lg.n)]
+    a = case("logistic_small_adapt", "logistic", {"n_rows": 400, "n_features": 8, "seed": 3}, q0s, [811], tune=250, draws=40,
+             adapt=True)
+    case("logistic_small_fixed", "logistic", {"n_rows": 400, "n_features": 8, "seed": 3}, [a["draws_q"][0, -1]], [812], tune=0,
+         draws=40, adapt=False, var=a["final_var"], eps=a["final_step_size"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "lockstep":
+        lockstep_cases()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "team":
         team_cases()
         raise SystemExit(0)

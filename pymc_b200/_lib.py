@@ -34,6 +34,8 @@ class ModelDesc(C.Structure):
         ("idx", C.c_void_p),
         ("y_u8", C.c_void_p),
         ("scalar0", C.c_double),
+        ("m1", C.c_void_p),
+        ("m2", C.c_void_p),
     ]
 
 

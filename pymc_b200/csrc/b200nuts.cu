@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include "dense.cuh"
+#include "lockstep.cuh"
 #include "models.cuh"
 #include "nuts_warp.cuh"
 
@@ -53,8 +55,24 @@ struct b200_model {
     EightSchoolsModel::Params eight{};
     RadonModel::Params radon{};
     StochVolModel::Params stochvol{};
-    ~b200_model() { for (void* p : owned) cudaFree(p); }
+    // lock-step (GEMM-shaped) models; every matrix is row-major with rows `ld` doubles apart (n rounded up to 4, zero pad)
+    long long ld = 0;
+    const double* prec = nullptr;   // MVGAUSS: precision P [n][ld]
+    const double* cov = nullptr;    // MVGAUSS: covariance Sigma [n][ld] (dense mass matrix)
+    const double* linvT = nullptr;  // MVGAUSS: L^-T [n][ld]   (p0 = L^-T z)
+    const double* chol = nullptr;   // MVGAUSS: L    [n][ld]   (v0 = Sigma p0 = L z)
+    double logp_const = 0.0;
+    const double* X = nullptr;      // LOGISTIC: design matrix [Npad][KP] row-major, zero padded (KP = 8, 32 or 128)
+    const uint8_t* y8 = nullptr;    // LOGISTIC: y[N]
+    long long n_rows = 0;
+    int KP = 0;
+    ~b200_model() {
+        for (void* p : owned) cudaFree(p);
+    }
 };
+
+static bool is_lockstep_kind(int kind);
+static int lockstep_logp(b200_model* m, const double* q_dev, int C, double* logp_dev, double* grad_dev, cudaStream_t st);
 
 template <class T>
 static int upload(b200_model* m, const std::vector<T>& h, const T** out) {
@@ -163,6 +181,52 @@ static int prepare_stochvol(b200_model* m, const b200_model_desc* d) {
     return upload(m, y2, &m->stochvol.y2);
 }
 
+template <class T>
+static int upload_raw(b200_model* m, const T* h, size_t count, const T** out) {
+    void* d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16)));
+    m->owned.push_back(d);
+    CU(cudaMemcpy(d, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(d);
+    return 0;
+}
+
+// host matrix [rows][cols] -> device [rows_pad][ld], zero padded
+static int upload_padded(b200_model* m, const double* h, size_t rows, size_t cols, size_t rows_pad, size_t ld, const double** out) {
+    void* d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(rows_pad * ld * sizeof(double), 16)));
+    m->owned.push_back(d);
+    if (rows_pad != rows || ld != cols) CU(cudaMemset(d, 0, rows_pad * ld * sizeof(double)));
+    CU(cudaMemcpy2D(d, ld * sizeof(double), h, cols * sizeof(double), cols * sizeof(double), rows, cudaMemcpyHostToDevice));
+    *out = static_cast<const double*>(d);
+    return 0;
+}
+
+static int prepare_mvgauss(b200_model* m, const b200_model_desc* d) {
+    const size_t n = (size_t)d->n;
+    if (!d->x || !d->aux || !d->m1 || !d->m2) return fail("mvgauss: prec, cov, L^-T and L are required");
+    m->ld = (long long)((n + 3) & ~(size_t)3);
+    const size_t ld = (size_t)m->ld;
+    if (upload_padded(m, d->x, n, n, n, ld, &m->prec) || upload_padded(m, d->aux, n, n, n, ld, &m->cov) ||
+        upload_padded(m, d->m1, n, n, n, ld, &m->linvT) || upload_padded(m, d->m2, n, n, n, ld, &m->chol))
+        return -1;
+    m->logp_const = -0.5 * (double)n * 1.8378770664093454836 - d->scalar0;  // -n/2 log 2pi - sum log L_ii
+    return 0;
+}
+
+static int prepare_logistic(b200_model* m, const b200_model_desc* d) {
+    if (!d->x || !d->y_u8 || d->n_obs <= 0) return fail("logistic: X and y are required");
+    if (d->n > 128) return fail("logistic: n_features=%d exceeds the fused kernel's limit (128)", d->n);
+    m->n_rows = d->n_obs;
+    m->ld = (d->n + 3) & ~3;
+    m->KP = d->n <= 8 ? 8 : (d->n <= 32 ? 32 : 128);
+    const size_t n_pad = (size_t)((d->n_obs + kLogiRows - 1) / kLogiRows) * kLogiRows;
+    if (upload_padded(m, d->x, (size_t)d->n_obs, (size_t)d->n, n_pad, (size_t)m->KP, &m->X) ||
+        upload_raw(m, d->y_u8, (size_t)d->n_obs, &m->y8))
+        return -1;
+    return 0;
+}
+
 extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) {
     if (!desc || !out) return fail("b200_model_create: null argument");
     if (desc->n <= 0) return fail("b200_model_create: n must be positive");
@@ -177,6 +241,8 @@ extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) 
         case B200_MODEL_EIGHT_SCHOOLS: rc = prepare_eight(m, desc); break;
         case B200_MODEL_RADON: rc = prepare_radon(m, desc); break;
         case B200_MODEL_STOCHVOL: rc = prepare_stochvol(m, desc); break;
+        case B200_MODEL_MVGAUSS: rc = prepare_mvgauss(m, desc); break;
+        case B200_MODEL_LOGISTIC: rc = prepare_logistic(m, desc); break;
         default: rc = fail("b200_model_create: model kind %d not implemented", desc->kind);
     }
     if (rc) {
@@ -339,8 +405,12 @@ extern "C" int b200_logp_dlogp(b200_model* m, const double* q, int32_t C, double
     if (stage_in(sl, logp, (size_t)C * sizeof(double), mem, false, true, st)) return -1;
     if (stage_in(sg, grad, vb, mem, false, true, st)) return -1;
     Timer t(st);
-    LogpLaunch L{m, C, (const double*)sq.ptr(), (double*)sl.ptr(), (double*)sg.ptr(), st};
-    if (dispatch(m, L)) return -1;
+    if (is_lockstep_kind(m->kind)) {
+        if (lockstep_logp(m, (const double*)sq.ptr(), C, (double*)sl.ptr(), (double*)sg.ptr(), st)) return -1;
+    } else {
+        LogpLaunch L{m, C, (const double*)sq.ptr(), (double*)sl.ptr(), (double*)sg.ptr(), st};
+        if (dispatch(m, L)) return -1;
+    }
     t.stop(1);
     if (stage_out(sl, st) || stage_out(sg, st)) return -1;
     CU(cudaStreamSynchronize(st));
@@ -373,6 +443,7 @@ extern "C" int b200_leapfrog(b200_model* m, const double* var, const double* eps
     if (!m || !var || !eps || !q || !p || !v || !grad || !energy || !logp || !idx)
         return fail("b200_leapfrog: null argument");
     if (n_steps < 0) return fail("b200_leapfrog: n_steps < 0");
+    if (is_lockstep_kind(m->kind)) return fail("b200_leapfrog: GEMM-shaped models advance in lock step inside b200_nuts_run");
     if (C <= 0) return 0;
     CU(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -394,6 +465,195 @@ extern "C" int b200_leapfrog(b200_model* m, const double* var, const double* eps
         stage_out(s_e, st) || stage_out(s_l, st) || stage_out(s_i, st))
         return -1;
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM-shaped models: batched evaluation of C points (rows of Q[C][ld]) -> G[C][ld] (+ logp[C]) with the
+// hand-written DMMA kernels of dense.cuh.
+// ------------------------------------------------------------------------------------------------
+template <int WM, int NB>
+static int launch_gemm(cudaStream_t st, const double* Q, long long ldq, int C, const double* M, long long ldm, int Nout, int K,
+                       double alpha, double* D, long long ldd) {
+    constexpr int NST = 3;
+    const size_t smem = NST * gemm_stage_doubles<WM, NB>() * sizeof(double);
+    auto kern = gemm_nt_dmma_kernel<WM, NB, NST>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((Nout + 8 * NB - 1) / (8 * NB), (C + 16 * WM - 1) / (16 * WM));
+    kern<<<grid, 32 * WM, smem, st>>>(Q, ldq, C, M, ldm, Nout, K, alpha, D, ldd);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// D[C][Nout] = alpha * Q[C][K] . M[Nout][K]^T.  Tile shape picked per call: chains per CTA from C, outputs per CTA
+// (8 NB) so that the tile count fills whole waves of 148 SMs.
+static int gemm_nt(cudaStream_t st, const double* Q, long long ldq, int C, const double* M, long long ldm, int Nout, int K,
+                   double alpha, double* D, long long ldd) {
+    if (C <= 0 || Nout <= 0) return 0;
+    const int wm = C > 64 ? 8 : (C > 32 ? 4 : 2);
+    const int cb = (C + 16 * wm - 1) / (16 * wm);
+    int best_nb = 9;
+    double best = -1.0;
+    const int nbs[3] = {17, 9, 5};
+    for (int i = 0; i < (wm == 8 ? 3 : 2); ++i) {
+        const int nb = (wm == 8) ? nbs[i] : nbs[i + 1];
+        const long long tiles = (long long)cb * ((Nout + 8 * nb - 1) / (8 * nb));
+        const long long waves = (tiles + 147) / 148;
+        // useful work / occupied SM time; small bonus for wider tiles (fewer fragment loads per DMMA)
+        const double eff = (double)Nout * cb / ((double)waves * 148 * 8 * nb) + 1e-3 * nb;
+        if (eff > best) { best = eff; best_nb = nb; }
+    }
+#define B200_GEMM(WM_, NB_) return launch_gemm<WM_, NB_>(st, Q, ldq, C, M, ldm, Nout, K, alpha, D, ldd)
+    if (wm == 8) { if (best_nb == 17) B200_GEMM(8, 17); if (best_nb == 9) B200_GEMM(8, 9); B200_GEMM(8, 5); }
+    if (wm == 4) { if (best_nb == 9) B200_GEMM(4, 9); B200_GEMM(4, 5); }
+    if (best_nb == 9) B200_GEMM(2, 9);
+    B200_GEMM(2, 5);
+#undef B200_GEMM
+}
+
+struct BatchScratch {  // logistic partial results
+    DevBuf gpart, lpart;
+    int gx = 0, cpad = 0;
+};
+
+static bool is_lockstep_kind(int kind) { return kind == B200_MODEL_MVGAUSS || kind == B200_MODEL_LOGISTIC; }
+
+template <int KB>
+static int launch_logistic(const b200_model* m, int C, const double* Q, long long ldq, BatchScratch& bs, cudaStream_t st) {
+    auto kern = logistic_fused_kernel<KB>;
+    const size_t smem = logistic_smem_bytes<KB>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<dim3(bs.gx, bs.cpad / kLogiChains), 256, smem, st>>>(m->X, m->y8, m->n_rows, Q, ldq, C, m->n, bs.gpart.as<double>(),
+                                                               bs.lpart.as<double>(), bs.cpad);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// G = grad logp(Q) for all C rows; logp written only for models that do not derive it from q.g
+static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* logp, BatchScratch& bs, cudaStream_t st,
+                      int* launches) {
+    const int n = m->n;
+    const long long ld = m->ld;
+    if (m->kind == B200_MODEL_MVGAUSS) {
+        // grad = -P q  (MvNormal.logp multivariate.py:275-295; P symmetric)
+        if (launches) *launches += 1;
+        return gemm_nt(st, Q, ld, C, m->prec, ld, n, (int)ld, -1.0, G, ld);
+    }
+    // logistic: one fused pass over X, then the fixed-order reduction of the row-CTA partials
+    const int cb = (C + kLogiChains - 1) / kLogiChains;
+    const long long n_slabs = (m->n_rows + kLogiRows - 1) / kLogiRows;
+    const int gx = (int)std::max<long long>(1, std::min<long long>(n_slabs, 148 / std::min(cb, 148)));
+    if (!bs.gpart.p || bs.gx != gx || bs.cpad != cb * kLogiChains) {
+        bs.gx = gx;
+        bs.cpad = cb * kLogiChains;
+        if (bs.gpart.p) { cudaFree(bs.gpart.p); bs.gpart.p = nullptr; }
+        if (bs.lpart.p) { cudaFree(bs.lpart.p); bs.lpart.p = nullptr; }
+        CU(bs.gpart.alloc((size_t)gx * bs.cpad * m->KP * sizeof(double)));
+        CU(bs.lpart.alloc((size_t)gx * bs.cpad * sizeof(double)));
+    }
+    int rc = 0;
+    switch (m->KP) {
+        case 8: rc = launch_logistic<1>(m, C, Q, ld, bs, st); break;
+        case 32: rc = launch_logistic<4>(m, C, Q, ld, bs, st); break;
+        default: rc = launch_logistic<16>(m, C, Q, ld, bs, st); break;
+    }
+    if (rc) return rc;
+    logistic_finish_kernel<<<(C + 3) / 4, 128, 0, st>>>(Q, ld, G, ld, n, m->KP, C, bs.cpad, bs.gpart.as<double>(),
+                                                        bs.lpart.as<double>(), gx, logp);
+    CU(cudaGetLastError());
+    if (launches) *launches += 2;
+    return 0;
+}
+
+// b200_logp_dlogp for the GEMM-shaped models: user rows [C][n] <-> padded rows [C][ld]
+static int lockstep_logp(b200_model* m, const double* q_dev, int C, double* logp_dev, double* grad_dev, cudaStream_t st) {
+    const int n = m->n;
+    const long long ld = m->ld;
+    DevBuf Qp, Gp;
+    CU(Qp.alloc((size_t)C * ld * sizeof(double)));
+    CU(Gp.alloc((size_t)C * ld * sizeof(double)));
+    CU(cudaMemsetAsync(Qp.p, 0, (size_t)C * ld * sizeof(double), st));
+    CU(cudaMemcpy2DAsync(Qp.p, ld * sizeof(double), q_dev, n * sizeof(double), n * sizeof(double), C, cudaMemcpyDeviceToDevice, st));
+    BatchScratch bs;
+    if (batch_eval(m, C, Qp.as<double>(), Gp.as<double>(), logp_dev, bs, st, nullptr)) return -1;
+    if (m->kind == B200_MODEL_MVGAUSS) {
+        half_dot_logp_kernel<<<(C + 3) / 4, 128, 0, st>>>(Qp.as<double>(), Gp.as<double>(), ld, n, C, m->logp_const, logp_dev);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpy2DAsync(grad_dev, n * sizeof(double), Gp.p, ld * sizeof(double), n * sizeof(double), C, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// The lock-step driver: advance <-> batched evaluation until every chain is done.
+static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
+    const int C = P.C, n = P.n;
+    const bool dense = P.dense != 0;
+    const long long ld = m->ld;
+    const size_t mat = (size_t)C * ld * sizeof(double);
+    DevBuf state, vecs, Qreq, Greq, Wreq, lreq, P0n, V0n, counters, mom_list, Zb, P0b, V0b;
+    P.ld = ld;
+    P.vec_stride = ls_vec_count(P.max_td) * n;
+    CU(state.alloc((size_t)C * sizeof(LsState)));
+    CU(vecs.alloc((size_t)C * P.vec_stride * sizeof(double)));
+    CU(Qreq.alloc(mat)); CU(Greq.alloc(mat)); CU(lreq.alloc((size_t)C * sizeof(double)));
+    CU(counters.alloc(2 * sizeof(int))); CU(mom_list.alloc((size_t)C * sizeof(int)));
+    CU(cudaMemsetAsync(Qreq.p, 0, mat, st)); CU(cudaMemsetAsync(Greq.p, 0, mat, st));
+    if (dense) {
+        CU(Wreq.alloc(mat)); CU(P0n.alloc(mat)); CU(V0n.alloc(mat)); CU(Zb.alloc(mat)); CU(P0b.alloc(mat)); CU(V0b.alloc(mat));
+        CU(cudaMemsetAsync(Wreq.p, 0, mat, st)); CU(cudaMemsetAsync(Zb.p, 0, mat, st));
+    }
+    CU(cudaMemsetAsync(vecs.p, 0, (size_t)C * P.vec_stride * sizeof(double), st));
+    P.state = state.as<LsState>(); P.vecs = vecs.as<double>();
+    P.Qreq = Qreq.as<double>(); P.Greq = Greq.as<double>(); P.Wreq = Wreq.as<double>(); P.logp_req = lreq.as<double>();
+    P.P0n = P0n.as<double>(); P.V0n = V0n.as<double>();
+    P.counters = counters.as<int>(); P.mom_list = mom_list.as<int>();
+    P.logp_from_dot = (m->kind == B200_MODEL_MVGAUSS) ? 1 : 0;
+    P.logp_const = m->logp_const;
+    BatchScratch bs;
+    const int blocks = (C + 3) / 4;
+    Timer t(st);
+    int launches = 0;
+    ls_init_kernel<<<blocks, 128, 0, st>>>(P);
+    CU(cudaGetLastError());
+    ++launches;
+    int n_mom = dense ? C : 0;  // every chain needs the momentum of draw 0
+    for (;;) {
+        if (batch_eval(m, C, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
+        if (dense) {
+            // w = Sigma g for every requested point (QuadPotentialFull.velocity, quadpotential.py:705-707)
+            if (gemm_nt(st, P.Greq, ld, C, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
+            ++launches;
+            if (n_mom > 0) {
+                ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb.as<double>());
+                // p0 = L^-T z (solve_triangular(chol.T, z), quadpotential.py:710-713);  v0 = Sigma p0 = L z
+                if (gemm_nt(st, Zb.as<double>(), ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b.as<double>(), ld)) return -1;
+                if (gemm_nt(st, Zb.as<double>(), ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b.as<double>(), ld)) return -1;
+                ls_scatter_mom_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, P0b.as<double>(), V0b.as<double>());
+                CU(cudaGetLastError());
+                launches += 4;
+            }
+        }
+        CU(cudaMemsetAsync(P.counters, 0, 2 * sizeof(int), st));
+        if (n > 512) ls_advance_kernel<8><<<C, 256, 0, st>>>(P);
+        else ls_advance_kernel<1><<<blocks, 128, 0, st>>>(P);
+        CU(cudaGetLastError());
+        ++launches;
+        int h[2];
+        CU(cudaMemcpyAsync(h, P.counters, sizeof h, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h[0] == 0) break;
+        n_mom = dense ? h[1] : 0;
+    }
+    t.stop(launches);
     return 0;
 }
 
@@ -447,8 +707,12 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     if (cfg->max_treedepth < 1 || cfg->max_treedepth > kMaxLevels || cfg->early_max_treedepth < 1 ||
         cfg->early_max_treedepth > cfg->max_treedepth)
         return fail("b200_nuts_run: treedepth must satisfy 1 <= early <= max <= %d", kMaxLevels);
-    if (cfg->mass_kind != B200_MASS_DIAG && cfg->mass_kind != B200_MASS_DIAG_ADAPT)
-        return fail("b200_nuts_run: mass kind %d not implemented for this model", cfg->mass_kind);
+    const bool lockstep = is_lockstep_kind(m->kind);
+    if (cfg->mass_kind == B200_MASS_DENSE) {
+        if (m->kind != B200_MODEL_MVGAUSS) return fail("b200_nuts_run: the dense mass matrix is the model's covariance (MVGAUSS only)");
+    } else if (cfg->mass_kind != B200_MASS_DIAG && cfg->mass_kind != B200_MASS_DIAG_ADAPT) {
+        return fail("b200_nuts_run: mass kind %d not implemented", cfg->mass_kind);
+    }
     if (cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER && !z)
         return fail("b200_nuts_run: momentum_source=HOST_BUFFER but z is null");
     if (!(cfg->step_scale > 0)) return fail("b200_nuts_run: step_scale must be > 0");
@@ -520,8 +784,21 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     P.rng = (b200_pcg64*)s_rng.ptr(); P.draws_out = (double*)s_draws.ptr();
     P.st = ds; P.sm = dsum;
 
-    NutsLaunch L{m, P, st};
-    if (dispatch(m, L)) return -1;
+    if (lockstep) {
+        LsDev Q{};
+        Q.C = C; Q.n = n; Q.tune = P.tune; Q.draws = P.draws; Q.max_td = P.max_td; Q.early_td = P.early_td;
+        Q.adapt_step = P.adapt_step; Q.mass_kind = P.mass_kind; Q.momentum_source = P.momentum_source;
+        Q.store_warmup = P.store_warmup; Q.window = P.window; Q.discard = P.discard; Q.chain_offset = P.chain_offset;
+        Q.dense = (cfg->mass_kind == B200_MASS_DENSE) ? 1 : 0;
+        Q.eps0 = P.eps0; Q.target = P.target; Q.gamma = P.gamma; Q.kappa = P.kappa; Q.t0 = P.t0; Q.Emax = P.Emax;
+        Q.init_weight = P.init_weight; Q.philox_seed = P.philox_seed;
+        Q.q0 = P.q0; Q.var0 = P.var0; Q.mean0 = P.mean0; Q.eps0c = P.eps0c; Q.z = P.z; Q.rng = P.rng;
+        Q.draws_out = P.draws_out; Q.st = P.st; Q.sm = P.sm;
+        if (run_lockstep(m, Q, st)) return -1;
+    } else {
+        NutsLaunch L{m, P, st};
+        if (dispatch(m, L)) return -1;
+    }
 
     if (stage_out(s_rng, st) || stage_out(s_draws, st)) return -1;
     for (auto& s : st_arr) if (stage_out(s, st)) return -1;

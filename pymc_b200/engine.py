@@ -55,7 +55,12 @@ class CompiledModel:
             d.n_obs = len(data["y"])
             d.y = hold(data["y"], np.float64)
         elif spec.name == "mvgauss":
+            import scipy.linalg as sl
+
+            L = np.ascontiguousarray(data["L"], dtype=np.float64)
+            Linv = sl.solve_triangular(L, np.eye(L.shape[0]), lower=True)
             d.x, d.aux = hold(data["prec"], np.float64), hold(data["cov"], np.float64)
+            d.m1, d.m2 = hold(Linv.T, np.float64), hold(L, np.float64)
             d.scalar0 = spec.meta["logdet_L"]
         handle = C.c_void_p()
         _lib.check(self._lib.b200_model_create(C.byref(d), C.byref(handle)))
@@ -131,7 +136,7 @@ class CompiledModel:
         cfg.chains, cfg.tune, cfg.draws = Cn, int(tune), int(draws)
         cfg.max_treedepth, cfg.early_max_treedepth = int(max_treedepth), int(early_max_treedepth)
         cfg.adapt_step_size = int(bool(adapt_step_size))
-        cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT}[mass]
+        cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT, "dense": _lib.MASS_DENSE}[mass]
         cfg.momentum_source = _lib.MOMENTUM_DEVICE_PHILOX if z is None else _lib.MOMENTUM_HOST_BUFFER
         cfg.store_warmup = int(bool(store_warmup))
         cfg.chain_offset = int(chain_offset)

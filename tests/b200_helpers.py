@@ -16,6 +16,10 @@ SPEC_OF = {
     "stochvol_small_adapt": lambda: models.stochvol(T=100, seed=4),
     "stochvol_small_fixed": lambda: models.stochvol(T=100, seed=4),
     "stochvol_fixed": models.stochvol,
+    "mvgauss_dense_fixed": lambda: models.mvgauss(n=60, seed=5),
+    "mvgauss_dense_stepadapt": lambda: models.mvgauss(n=60, seed=5),
+    "logistic_small_adapt": lambda: models.logistic(n_rows=400, n_features=8, seed=3),
+    "logistic_small_fixed": lambda: models.logistic(n_rows=400, n_features=8, seed=3),
 }
 TREE_KW = {"radon_small_adapt": dict(max_treedepth=6, early_max_treedepth=4)}
 DISCRETE = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_max_treedepth"]
@@ -47,7 +51,14 @@ def gpu_free_run(cm, d, name, draws=None):
         assert draws <= tune or tune == 0
         T = draws
     kw = dict(TREE_KW.get(name, {}))
-    if bool(d["adapt"]):
+    dense = bool(d["dense"]) if "dense" in d else False
+    if dense:
+        kw.update(mass="dense", adapt_step_size=bool(d["adapt"]))
+        if bool(d["adapt"]):
+            t, dr = (T, 0) if draws is not None else (tune, int(d["draws"]))
+        else:
+            t, dr = 0, T
+    elif bool(d["adapt"]):
         kw.update(mass="diag_adapt", mean0=d["q0"], var0=d["init_var"], adapt_step_size=True, step_scale=float(d["step_scale"]))
         t, dr = (T, 0) if draws is not None else (tune, int(d["draws"]))
     else:

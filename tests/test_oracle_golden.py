@@ -8,8 +8,9 @@ from b200_helpers import SPEC_OF, TREE_KW
 from oracle import logp_numpy, nuts_numpy
 
 
-def _oracle(spec, f, var, adapt=False, **kw):
-    return nuts_numpy.Oracle(f, nuts_numpy.DiagMass(var, adapt=adapt), adapt_step_size=False, **kw)
+def _oracle(spec, f, var, adapt=False, dense=False, **kw):
+    mass = nuts_numpy.DenseMass(spec.data["cov"]) if dense else nuts_numpy.DiagMass(var, adapt=adapt)
+    return nuts_numpy.Oracle(f, mass, adapt_step_size=False, **kw)
 
 
 def _gen_from_state(state_u64x4):
@@ -23,13 +24,14 @@ def _gen_from_state(state_u64x4):
 
 
 @pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "std_normal_team_fixed",
-                                  "stochvol_small_fixed", "stochvol_fixed"])
+                                  "stochvol_small_fixed", "stochvol_fixed", "logistic_small_fixed",
+                                  "mvgauss_dense_fixed"])
 def test_fixed_step_chains_reproduce_golden(golden, name):
     d = golden(name)
     spec = SPEC_OF[name]()
     f = logp_numpy.make_logp(spec)
     for c in range(len(d["seeds"])):
-        o = _oracle(spec, f, d["var"][c])
+        o = _oracle(spec, f, d["var"][c], dense=bool(d["dense"]) if "dense" in d else False)
         o.da = nuts_numpy.DualAveraging(float(d["used_eps"][c][0]))
         o.rng, o.tune = _gen_from_state(d["pre_rng"][c][0]), False
         qs, st = o.run(d["q0"][c], 0, int(d["draws"]), z=d["z"][c])

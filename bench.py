@@ -4,6 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA engine (this repo)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
 
+`--workload {radon,logistic,stochvol,mvgauss}` selects the BASELINE config (default: #2, the one the metric is quoted
+on for a single GPU; the defaults of the others are sized so a step takes seconds).
 One "step" = one complete sampling run of BASELINE config #2 on each GPU: Radon hierarchical regression
 (919 obs, 85 counties, n=175, fp64), 2048 chains x (1000 tune + 1000 draws), jitter+adapt_diag, inside ONE
 persistent kernel launch per GPU.  N > 1 shards chains (2048 per GPU, weak scaling, no data-path
@@ -35,6 +37,38 @@ METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
 ALG_BYTES_PER_EVAL = 919 * (8 + 8 + 4) + 7 * 175 * 8  # observed data + state traffic = 28,180 B
 
+# The bench line (no --workload) is BASELINE config #2, the configuration the metric is quoted on for ONE GPU.
+# The other BASELINE configs can be timed with --workload; per-eval algorithmic work follows SURVEY 8(d).
+WORKLOADS = {
+    "radon": dict(
+        builder="radon", args={}, chains=2048, tune=1000, draws=1000, scaling="weak", mass="diag_adapt",
+        bound="hbm", per_eval=float(ALG_BYTES_PER_EVAL), kernel="nuts_warp_kernel<RadonModel,6>",
+        desc={"n": 175, "n_obs": 919, "counties": 85}, cpu_procs=0, cpu_tune=300, cpu_draws=200,
+        l2="outputs (2.9 GB of draws per step) exceed L2; no explicit flush needed",
+        note="observed data is staged once per CTA into shared memory (bulk TMA) and the chain state lives in "
+             "registers/shared memory, so DRAM traffic is far below the algorithmic bytes; the binding pipe is fp64"),
+    "logistic": dict(  # config #3: 512 chains per GPU (4096 over 8), X replicated
+        builder="logistic", args={}, chains=512, tune=60, draws=20, scaling="weak", mass="diag_adapt",
+        bound="tensor", per_eval=4.0 * 1e6 * 128, kernel="logistic_fused_kernel<16> (fp64 DMMA)",
+        desc={"n": 128, "n_rows": 1_000_000}, cpu_procs=16, cpu_tune=12, cpu_draws=6,
+        l2="the design matrix (1.02 GB) is streamed from HBM on every batched leapfrog and exceeds L2",
+        note="lock-step batched leapfrog: one fused pass over X per batch (X.beta, sigmoid/softplus, X^T r) on the fp64 "
+             "tensor path (mma.sync m8n8k4.f64); flops per grad-eval per chain = 4 N K"),
+    "stochvol": dict(  # config #4: 256 chains per GPU (512 over 2), deep trees
+        builder="stochvol", args={}, chains=256, tune=300, draws=100, scaling="weak", mass="diag_adapt",
+        bound="hbm", per_eval=24000.0 + 7 * 3003 * 8 + 2 * 3003 * 8 * 2, kernel="nuts_warp_kernel<StochVolModel,12,8> (chain = CTA)",
+        desc={"n": 3003, "T": 3000}, cpu_procs=0, cpu_tune=40, cpu_draws=20,
+        l2="tree bookkeeping of 256 chains (53 vectors x 24 KB each) is spread over HBM/L2",
+        note="chain = CTA of 8 warps; integrator state in shared memory, pending-subtree stack in HBM/L2"),
+    "mvgauss": dict(  # config #5: 256 chains in TOTAL, strong scaling over GPUs, dense mass matrix
+        builder="mvgauss", args={}, chains=256, tune=20, draws=10, scaling="strong", mass="dense",
+        bound="tensor", per_eval=4.0 * 1e4 * 1e4, kernel="gemm_nt_dmma_kernel (fp64 DMMA)",
+        desc={"n": 10000, "mass": "QuadPotentialFull(Sigma)"}, cpu_procs=8, cpu_tune=3, cpu_draws=2,
+        l2="precision and covariance (800 MB each) are streamed from HBM on every batched leapfrog and exceed L2",
+        note="lock-step batched leapfrog: grad = -P q and w = Sigma g as two NT GEMMs over all chains on the fp64 tensor "
+             "path; flops per grad-eval per chain = 4 n^2 (one mass GEMM per leapfrog by linearity)"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,34 +76,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains-per-gpu", type=int, default=2048)
-    ap.add_argument("--tune", type=int, default=1000)
-    ap.add_argument("--draws", type=int, default=1000)
+    ap.add_argument("--workload", default="radon", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains-per-gpu", type=int, default=0, help="0 = the workload's default")
+    ap.add_argument("--tune", type=int, default=-1)
+    ap.add_argument("--draws", type=int, default=-1)
     ap.add_argument("--cpu-chains", type=int, default=0, help="reference arm / cpu_baseline: chains per step (0 = host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.wl = WORKLOADS[args.workload]
+    args.tune = args.wl["tune"] if args.tune < 0 else args.tune
+    args.draws = args.wl["draws"] if args.draws < 0 else args.draws
+    return args
+
+
+def workload_name(args, C):
+    base = {"radon": "radon_hierarchical", "logistic": "logistic_glm_1e6x128", "stochvol": "stochastic_volatility_T3000",
+            "mvgauss": "gaussian_n10000_dense_mass"}[args.workload]
+    return f"{base}_{C}chains_{args.tune}tune_{args.draws}draws"
 
 
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores, one process per chain
 # ---------------------------------------------------------------------------------------------
-def _cpu_chain(job):
-    seed, tune, draws = job
-    try:  # one BLAS thread per chain process, as the reference does (sampling/parallel.py:200-205)
-        from threadpoolctl import threadpool_limits
+_CPU_SPEC = {}
 
-        threadpool_limits(limits=1)
+
+def _cpu_chain(job):
+    seed, tune, draws, workload, threads = job
+    try:  # BLAS threads per chain process (the reference pins 1 per chain, sampling/parallel.py:200-205; the
+        from threadpoolctl import threadpool_limits  # BLAS-bound configs get cores/processes threads each)
+
+        threadpool_limits(limits=threads)
     except Exception:
         pass
     from oracle import logp_numpy, nuts_numpy
     from pymc_b200 import models
 
-    spec = models.radon()
+    wl = WORKLOADS[workload]
+    if workload not in _CPU_SPEC:  # built once per worker process
+        _CPU_SPEC[workload] = models.BUILDERS[wl["builder"]](**wl["args"])
+    spec = _CPU_SPEC[workload]
     f = logp_numpy.make_logp(spec)
     rng = np.random.default_rng(seed)
     q0 = spec.initial_point() + rng.uniform(-1, 1, spec.n)
-    mass = nuts_numpy.DiagMass(np.ones(spec.n), adapt=True, initial_mean=q0.copy(), initial_weight=10)
+    if wl["mass"] == "dense":
+        mass = nuts_numpy.DenseMass(spec.data["cov"])
+    else:
+        mass = nuts_numpy.DiagMass(np.ones(spec.n), adapt=True, initial_mean=q0.copy(), initial_weight=10)
     o = nuts_numpy.Oracle(f, mass)
     o.setup_chain(np.random.default_rng(seed + 1))
     t0 = time.perf_counter()
@@ -77,9 +131,9 @@ def _cpu_chain(job):
     return int(st["tree_size"].sum()), time.perf_counter() - t0, qs[tune:, :4]
 
 
-def cpu_run(chains, tune, draws, seed0, pool):
+def cpu_run(chains, tune, draws, seed0, pool, workload="radon", threads=1):
     t0 = time.perf_counter()
-    out = pool.map(_cpu_chain, [(seed0 + 2 * c, tune, draws) for c in range(chains)])
+    out = pool.map(_cpu_chain, [(seed0 + 2 * c, tune, draws, workload, threads) for c in range(chains)])
     wall = time.perf_counter() - t0
     evals = sum(o[0] for o in out)
     return evals, wall, np.stack([o[2] for o in out])
@@ -92,33 +146,43 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_plan(args):
+    """processes, BLAS threads per process, chains, tune, draws of the bounded CPU sample of this workload."""
+    cores = host_cores()
+    wl = args.wl
+    procs = min(cores, wl["cpu_procs"] or cores)
+    chains = args.cpu_chains or procs
+    procs = min(procs, chains)
+    return procs, max(1, cores // procs), chains, min(args.tune, wl["cpu_tune"]), min(args.draws, wl["cpu_draws"])
+
+
 def reference_arm(args):
     import multiprocessing as mp
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = host_cores()
-    chains = args.cpu_chains or cores
+    procs, threads, chains, tune, draws = cpu_plan(args)
+    cores = procs * threads
     # bounded sample: `chains` chains x (tune + draws) shortened so a step is ~10-20 s of wall time
-    tune, draws = min(args.tune, 300), min(args.draws, 200)
-    with mp.get_context("spawn").Pool(min(cores, chains)) as pool:
-        for _ in range(max(args.warmup, 1) if args.warmup else 0):
-            cpu_run(min(chains, cores), 20, 10, 999, pool)
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for _ in range(1 if args.warmup else 0):  # imports, model build (and BLAS warm-up) in every worker
+            cpu_run(procs, 2, 1, 999, pool, args.workload, threads)
         evals, wall = 0, 0.0
         for s in range(args.steps):
-            e, w, _ = cpu_run(chains, tune, draws, 1000 * (s + 1), pool)
+            e, w, _ = cpu_run(chains, tune, draws, 1000 * (s + 1), pool, args.workload, threads)
             evals += e
             wall += w
     value = evals / wall
-    sample = f"{chains} chains x ({tune} tune + {draws} draws) Radon per step, one process per chain on {min(cores, chains)} cores"
+    sample = (f"{chains} chains x ({tune} tune + {draws} draws) of the same {args.workload} model per step, {procs} processes x "
+              f"{threads} BLAS threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "radon_hierarchical_2048chains_1000tune_1000draws", "n": 175, "n_obs": 919,
-                   "counties": 85, "note": "bounded CPU sample of the same workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, chains), "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args, (args.chains_per_gpu or args.wl["chains"])), **args.wl["desc"],
+                   "note": "bounded CPU sample of the same workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,16 +277,24 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    spec = models.radon()
+    wl = args.wl
+    spec = models.BUILDERS[wl["builder"]](**wl["args"])
     cm = engine.CompiledModel(spec, device=local)
-    C, tune, draws, n = args.chains_per_gpu, args.tune, args.draws, spec.n
-    chains_total = C * world
-    lo = rank * C
+    tune, draws, n = args.tune, args.draws, spec.n
+    if wl["scaling"] == "strong":  # fixed total number of chains, split over the ranks (BASELINE config #5)
+        chains_total = args.chains_per_gpu * world if args.chains_per_gpu else wl["chains"]
+        lo, hi = parallel.chain_range(chains_total, rank, world)
+        C = hi - lo
+    else:
+        C = args.chains_per_gpu or wl["chains"]
+        chains_total = C * world
+        lo = rank * C
+    run_kw = dict(mass=wl["mass"])
     # streams and starts exactly as sample_b200_nuts derives them; global chain ids => independent of N
     step_rngs, _, jitter_seeds = brng.chain_generators(20260922, chains_total)
     q0_host = np.stack([spec.initial_point() + np.random.default_rng(s).uniform(-1, 1, n) for s in jitter_seeds[lo:lo + C]])
     mean_all = np.mean([spec.initial_point() + np.random.default_rng(s).uniform(-1, 1, n) for s in jitter_seeds], axis=0)
-    mean0_host = np.broadcast_to(mean_all, (C, n)).copy()
+    mean0_host = np.broadcast_to(mean_all, (C, n)).copy() if wl["mass"] == "diag_adapt" else None
     states0 = brng.pack_pcg64(step_rngs[lo:lo + C])
 
     def barrier():
@@ -232,12 +304,12 @@ def b200_arm(args):
 
     # ---- value: inputs resident in HBM, outputs stay in HBM --------------------------------------
     q0_d = torch.as_tensor(q0_host, device=dev)
-    mean0_d = torch.as_tensor(mean0_host, device=dev)
+    mean0_d = None if mean0_host is None else torch.as_tensor(mean0_host, device=dev)
     states = states0.copy()
 
     def step_device(k):
         return cm.nuts_run(q0_d, states, tune=tune, draws=draws, mean0=mean0_d, store_warmup=False,
-                           philox_seed=1000 + k, device_outputs=True, chain_offset=lo)
+                           philox_seed=1000 + k, device_outputs=True, chain_offset=lo, **run_kw)
 
     for k in range(args.warmup):
         res = step_device(-1 - k)
@@ -248,15 +320,20 @@ def b200_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evals_t = torch.zeros((), dtype=torch.int64, device=dev)
     all_evals_t = torch.zeros((), dtype=torch.int64, device=dev)
-    kernel_ms = []
+    kernel_ms, launches = [], 0
+    lockstep = args.workload in ("logistic", "mvgauss")
+    # start-state evaluations per chain: one per iteration (compute_state, base_hmc.py:202); the lock-step engine carries
+    # the accepted proposal's (logp, grad) into the next draw and evaluates only the very first start state
+    start_evals = 1 if lockstep else (tune + draws)
     ev0.record()
     for k in range(args.steps):
         res = step_device(k)
         # leapfrog gradient evaluations of ALL iterations (warm-up included): the kernel's own count minus the
-        # one start-state evaluation per iteration (compute_state, base_hmc.py:202)
+        # start-state evaluations
         all_evals_t += res.summary["grad_evals"].sum()
-        evals_t += res.summary["grad_evals"].sum() - C * (tune + draws)
+        evals_t += res.summary["grad_evals"].sum() - C * start_evals
         kernel_ms.append(res.kernel_ms)
+        launches += res.launches
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -277,72 +354,83 @@ def b200_arm(args):
         T = draws
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
         q0_p = pin((C, n), torch.float64); q0_p[:] = q0_host
-        mean0_p = pin((C, n), torch.float64); mean0_p[:] = mean0_host
+        mean0_p = None
+        if mean0_host is not None:
+            mean0_p = pin((C, n), torch.float64); mean0_p[:] = mean0_host
         n_e2e = max(1, min(args.steps, 3))
         st_e = states0.copy()
         # one untimed call: allocates the pooled pinned output buffers the timed calls reuse
         res_h = cm.nuts_run(q0_p, st_e, tune=tune, draws=draws, mean0=mean0_p, store_warmup=False,
-                            philox_seed=1999, device_outputs=False, chain_offset=lo, pinned_outputs=True)
+                            philox_seed=1999, device_outputs=False, chain_offset=lo, pinned_outputs=True, **run_kw)
         barrier()
         t0 = time.perf_counter()
         ev_tot = 0
         for k in range(n_e2e):
             res_h = cm.nuts_run(q0_p, st_e, tune=tune, draws=draws, mean0=mean0_p, store_warmup=False,
-                                philox_seed=2000 + k, device_outputs=False, chain_offset=lo, pinned_outputs=True)
-            ev_tot += int(res_h.summary["grad_evals"].sum()) - C * (tune + draws)
+                                philox_seed=2000 + k, device_outputs=False, chain_offset=lo, pinned_outputs=True, **run_kw)
+            ev_tot += int(res_h.summary["grad_evals"].sum()) - C * start_evals
         torch.cuda.synchronize()
         dt = parallel.max_over_ranks(time.perf_counter() - t0)
         ev_all = parallel.sum_over_ranks(float(ev_tot))
-        h2d = q0_p.nbytes + mean0_p.nbytes + st_e.nbytes
+        h2d = q0_p.nbytes + (mean0_p.nbytes if mean0_p is not None else 0) + st_e.nbytes
         d2h = res_h.draws.nbytes + sum(v.nbytes for v in res_h.stats.values()) + sum(v.nbytes for v in res_h.summary.values()) + st_e.nbytes
         e2e = {"value": ev_all / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e}
 
-    # ---- roofline of the dominant (only) kernel -------------------------------------------------------
-    peak, how = measured_peaks()
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
     k_ms = float(np.mean(kernel_ms))
-    achieved = ALG_BYTES_PER_EVAL * (all_evals / args.steps) / (k_ms * 1e-3) / 1e9
-    fp64 = None
+    per_launch = all_evals / args.steps  # grad evaluations of one run on this rank, start states included
+    fp64 = dmma = None
     if rank == 0:
         import ctypes
 
         tf = ctypes.c_double()
         if _lib.load().b200_measure_fp64_tflops(ctypes.byref(tf)) == 0:
             fp64 = tf.value
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(all_evals / args.steps), "peak_source": how,
-                "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch", "kernel": "nuts_warp_kernel<RadonModel,6>",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
-                "note": "observed data is staged once per CTA into shared memory (bulk TMA) and the chain state lives in "
-                        "registers/shared memory, so DRAM traffic is far below the algorithmic bytes; the binding pipe is fp64",
-                "fp64_peak_tflops_measured": fp64}
+        if _lib.load().b200_measure_dmma_tflops(ctypes.byref(tf)) == 0:
+            dmma = tf.value
+    if wl["bound"] == "hbm":
+        peak, how = measured_peaks()
+        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(per_launch) if args.workload == "radon" else None, "peak_source": how,
+                    "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch",
+                    "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_bytes_per_eval": wl["per_eval"], "note": wl["note"],
+                    "fp64_peak_tflops_measured": fp64}
+    else:  # dense contraction on the fp64 tensor path: no fp64 entry in MEASURED_PEAKS.json (HBM + bf16 only), so the
+        # denominator is the DMMA rate measured in this process by the library's own micro-benchmark
+        peak = dmma or 37.0
+        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "fp64 DMMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)"
+                    if dmma else "fallback 37.0 (scripts/mb/dmma.cu measured on this pool)",
+                    "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "note": wl["note"],
+                    "fp64_dfma_peak_tflops_measured": fp64,
+                    "time_base": "kernel_ms spans every launch of the lock-step loop (advance kernels and ragged tail included)"}
 
     # ---- cpu_baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
 
-        cores = host_cores()
-        chains = args.cpu_chains or cores
-        ct, cd = min(tune, 300), min(draws, 200)
-        with mp.get_context("spawn").Pool(min(cores, chains)) as pool:
-            cpu_run(min(chains, cores), 10, 5, 999, pool)  # import warm-up
-            e, w, qs = cpu_run(chains, ct, cd, 12345, pool)
-        cpu = {"value": e / w, "unit": UNIT, "cores": min(cores, chains), "kind": "port",
-               "sample": f"{chains} chains x ({ct} tune + {cd} draws) of the same Radon model, one process per chain",
-               "wall_s": w}
+        procs, threads, chains, ct, cd = cpu_plan(args)
+        with mp.get_context("spawn").Pool(procs) as pool:
+            cpu_run(procs, 2, 1, 999, pool, args.workload, threads)  # import / model-build warm-up
+            e, w, qs = cpu_run(chains, ct, cd, 12345, pool, args.workload, threads)
+        cpu = {"value": e / w, "unit": UNIT, "cores": procs * threads, "kind": "port",
+               "sample": f"{chains} chains x ({ct} tune + {cd} draws) of the same {args.workload} model, {procs} processes x "
+                         f"{threads} BLAS threads", "wall_s": w}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "radon_hierarchical_2048chains_1000tune_1000draws" if (C, tune, draws) == (2048, 1000, 1000)
-                       else f"radon_hierarchical_{C}chains_{tune}tune_{draws}draws",
-                       "n": n, "n_obs": 919, "counties": 85, "chains_per_gpu": C, "tune": tune, "draws": draws,
-                       "init": "jitter+adapt_diag", "momentum": "device philox",
-                       "l2": "outputs (2.9 GB of draws per step) exceed L2; no explicit flush needed"},
-            "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "config": {"workload": workload_name(args, C if wl["scaling"] == "weak" else chains_total), **wl["desc"],
+                       "chains_per_gpu": C, "chains_total": chains_total, "tune": tune, "draws": draws,
+                       "init": "jitter+adapt_diag" if wl["mass"] == "diag_adapt" else "jitter, fixed dense mass matrix",
+                       "momentum": "device philox", "l2": wl["l2"]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "ess": {"min_bulk_ess_last_step": ess_min, "ess_per_sec": ess_min / step_s, "chains": C, "draws": draws},
             "grad_evals_incl_start_state": all_evals * world, "divergent_fraction": div_frac,
         }

@@ -197,6 +197,9 @@ int b200_last_kernel_ms(double* ms, int32_t* launches);
 /* fp64 FMA micro-benchmark: sustained DFMA throughput in TFLOP/s of this device (roofline
  * denominator for compute-bound configs; MEASURED_PEAKS.json has only HBM and bf16). */
 int b200_measure_fp64_tflops(double* tflops);
+/* The same for the fp64 tensor path (mma.sync m8n8k4.f64, SASS DMMA.8x8x4) that the GEMM-shaped models
+ * (LOGISTIC, MVGAUSS) contract on. */
+int b200_measure_dmma_tflops(double* tflops);
 
 #ifdef __cplusplus
 }

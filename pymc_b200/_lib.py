@@ -125,6 +125,7 @@ SYMBOLS = [
     ),
     ("b200_last_kernel_ms", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     ("b200_measure_fp64_tflops", C.c_int, [C.POINTER(C.c_double)]),
+    ("b200_measure_dmma_tflops", C.c_int, [C.POINTER(C.c_double)]),
 ]
 
 _lib = None

@@ -846,3 +846,41 @@ extern "C" int b200_measure_fp64_tflops(double* tflops) {
     *tflops = best;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fp64 tensor-path (DMMA m8n8k4) peak micro-benchmark: roofline denominator of the GEMM-shaped configs
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = threadIdx.x * 1e-9, b = 1.0000001;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int b200_measure_dmma_tflops(double* tflops) {
+    if (!tflops) return fail("null argument");
+    const int blocks = 148 * 2, threads = 256, iters = 1 << 12;
+    DevBuf out;
+    CU(out.alloc((size_t)blocks * threads * sizeof(double)));
+    dmma_peak_kernel<<<blocks, threads>>>(out.as<double>(), 16);
+    CU(cudaDeviceSynchronize());
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        Timer t(0);
+        dmma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
+        CU(cudaGetLastError());
+        t.stop(1);
+        const double flops = 2.0 * 256.0 * 8.0 * (double)iters * blocks * (threads / 32);  // 8x8x4 FMAs per DMMA
+        best = std::max(best, flops / (g_last_ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return 0;
+}

@@ -128,6 +128,7 @@ def sample_b200_nuts(
     spec = cm.spec
     nk = dict(nuts_kwargs or {})
     nk.setdefault("target_accept", target_accept)
+    mass = nk.pop("mass", "diag_adapt")  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
 
     from . import parallel
 
@@ -142,7 +143,7 @@ def sample_b200_nuts(
 
     t0 = time.perf_counter()
     res = cm.nuts_run(q0_all[lo:hi], states, tune=tune, draws=draws, mean0=mean0, z=z, philox_seed=seed_key,
-                      store_warmup=not discard_tuned_samples, mass="diag_adapt", chain_offset=lo, **nk)
+                      store_warmup=not discard_tuned_samples, mass=mass, chain_offset=lo, **nk)
     sampling_time = time.perf_counter() - t0
     bad = res.summary["bad_energy_at"]
     if np.any(bad >= 0):

@@ -131,10 +131,11 @@ static int prepare_radon(b200_model* m, const b200_model_desc* d) {
         row_off[j] = K;
         for (int l = 0; l < 32 && (size_t)(j * 32 + l) < order.size(); ++l)
             row_len[j] = std::max<int>(row_len[j], (int)members[order[j * 32 + l]].size());
+        row_len[j] = (row_len[j] + 3) & ~3;  // whole blocks of 4 observations
         K += row_len[j];
     }
+    K += 4;  // the block the kernel prefetches past the last row
     if (K >= 0xffff) return fail("radon: padded observation rows exceed 65534");
-    K = std::max(K, 1);
     std::vector<double2> xy((size_t)K * 32, make_double2(0.0, 0.0));
     for (int j = 0; j < M; ++j) {
         for (int l = 0; l < 32 && (size_t)(j * 32 + l) < order.size(); ++l) {
@@ -143,7 +144,7 @@ static int prepare_radon(b200_model* m, const b200_model_desc* d) {
             for (int i : members[c]) xy[(size_t)(k++) * 32 + l] = make_double2(d->x[i], d->y[i]);
             seg[(size_t)j * 32 + l] = ((int32_t)members[c].size() << 16) | c;
         }
-        seg[(size_t)M * 32 + j] = (row_off[j] << 16) | row_len[j];
+        seg[(size_t)M * 32 + j] = (row_off[j] << 16) | (row_len[j] / 4);
     }
     RadonModel::Params& P = m->radon;
     P.K = K; P.M = M; P.J = J; P.n_obs = (int)N; P.E = (int)empty.size();

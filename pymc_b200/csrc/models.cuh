@@ -25,7 +25,7 @@ struct StdNormalModel {
     };
     __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
     __device__ static void stage(const Params&, char*, uint64_t*) {}
-    template <int NPL, int W>
+    template <int NPL, int W, bool SMALL = false>
     __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int tid, double* red) {
         double s = 0.0;
 #pragma unroll
@@ -55,7 +55,7 @@ struct EightSchoolsModel {
     };
     __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
     __device__ static void stage(const Params&, char*, uint64_t*) {}
-    template <int NPL, int W>
+    template <int NPL, int W, bool SMALL = false>
     __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int lane, double*) {
         static_assert(W == 1, "EightSchoolsModel is a chain-per-warp model");
         const double mu = q_s[0], ltau = q_s[1];
@@ -101,9 +101,10 @@ struct EightSchoolsModel {
 // ------------------------------------------------------------------------------------------------
 struct RadonModel {
     struct Params {
-        const double2* xy;   // [K][32]  (floor_i, y_i); row j occupies k in [off_j, off_j + len_j)
+        const double2* xy;   // [K][32]  (floor_i, y_i); row j occupies 4 * nblk_j consecutive k, rows back to back,
+                             //          followed by 4 all-zero k (the block prefetched past the last row)
         const int32_t* seg;  // [M][32]  (count << 16) | county, county = 0xffff: lane idle in this row
-                             // followed by rows[M]: (off_j << 16) | len_j   (padded to a multiple of 4 ints)
+                             // followed by rows[M]: (off_j << 16) | nblk_j   (padded to a multiple of 4 ints)
         const int32_t* empty;  // [E] counties without observations (prior terms only)
         int K, M, J, n_obs, E;
     };
@@ -123,7 +124,7 @@ struct RadonModel {
         }
     }
 
-    template <int NPL, int W>
+    template <int NPL, int W, bool SMALL = false>
     __device__ B200_EVAL_INLINE static double eval(const Params& P, const char* smem, const double* q_s, double* g_s, int lane,
                                                    double*) {
         static_assert(W == 1, "RadonModel is a chain-per-warp model");
@@ -151,28 +152,40 @@ struct RadonModel {
 
         // acc: S2, sum Ga, sum a*Ga, sum Gb, sum b*Gb, sum a^2, sum b^2   (Ga/Gb raw: sums of residuals)
         double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        // Rows are padded to multiples of 4 observations and stored back to back, so the whole data set is ONE stream of
+        // 4-observation blocks: the next block (of this row or of the next one; 4 zero blocks follow the last row) is
+        // loaded while the current one is consumed, and even/odd observations feed two independent accumulator sets.
+        const double2* ptr = xy;
+        double2 c0 = ptr[0], c1 = ptr[32], c2 = ptr[64], c3 = ptr[96];
         for (int j = 0; j < P.M; ++j) {
-            const int rw = rows[j];
-            const int len = rw & 0xffff;
-            const double2* row = xy + (rw >> 16) * 32;
+            const int nblk = rows[j] & 0xffff;
             const int sg = seg[j * 32 + lane];
             const int cnt = sg >> 16, c = sg & 0xffff;
             const bool live = c != 0xffff;
             const int ci = live ? c : 0;
             const double a_c = q_s[4 + ci], b_c = q_s[4 + J + ci];
             const double al = fma(sa, a_c, mu_a), be = fma(sb, b_c, mu_b);
-            double Ga = 0.0, Gb = 0.0, S2 = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < len; ++k) {
-                const double2 d = row[k * 32];
-                const double r = d.y - fma(be, d.x, al);
-                if (k < cnt) {  // padding of the row is skipped (predicated, no branch)
-                    S2 = fma(r, r, S2);
-                    Ga += r;
-                    Gb = fma(r, d.x, Gb);
-                }
+            double Ga0 = 0.0, Gb0 = 0.0, S20 = 0.0, Ga1 = 0.0, Gb1 = 0.0, S21 = 0.0;
+            // SMALL: no unrolling inside the persistent NUTS kernel, whose hot code must stay inside the instruction cache
+            // (measured: 511 vs 562 ms per bench step); the stand-alone leapfrog/logp kernels unroll (540 vs 393 M evals/s)
+#pragma unroll(SMALL ? 1 : 4)
+            for (int b = 0, kb = 0; b < nblk; ++b, kb += 4) {
+                ptr += 128;
+                const double2 n0 = ptr[0], n1 = ptr[32], n2 = ptr[64], n3 = ptr[96];
+                double r0 = c0.y - fma(be, c0.x, al), r1 = c1.y - fma(be, c1.x, al);
+                double r2 = c2.y - fma(be, c2.x, al), r3 = c3.y - fma(be, c3.x, al);
+                r0 = (kb < cnt) ? r0 : 0.0;  // padding of the row contributes exact zeros
+                r1 = (kb + 1 < cnt) ? r1 : 0.0;
+                r2 = (kb + 2 < cnt) ? r2 : 0.0;
+                r3 = (kb + 3 < cnt) ? r3 : 0.0;
+                S20 = fma(r0, r0, S20); Ga0 += r0; Gb0 = fma(r0, c0.x, Gb0);
+                S21 = fma(r1, r1, S21); Ga1 += r1; Gb1 = fma(r1, c1.x, Gb1);
+                S20 = fma(r2, r2, S20); Ga0 += r2; Gb0 = fma(r2, c2.x, Gb0);
+                S21 = fma(r3, r3, S21); Ga1 += r3; Gb1 = fma(r3, c3.x, Gb1);
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }
-            acc[0] += S2;
+            const double Ga = Ga0 + Ga1, Gb = Gb0 + Gb1;
+            acc[0] += S20 + S21;
             if (live) {  // county finished: its two gradient entries are complete
                 g_s[4 + c] = fma(sa_ie2, Ga, -a_c);
                 g_s[4 + J + c] = fma(sb_ie2, Gb, -b_c);
@@ -228,7 +241,7 @@ struct StochVolModel {
     };
     __host__ __device__ static size_t shared_bytes(const Params&) { return 0; }
     __device__ static void stage(const Params&, char*, uint64_t*) {}
-    template <int NPL, int W>
+    template <int NPL, int W, bool SMALL = false>
     __device__ static double eval(const Params& P, const char*, const double* q_s, double* g_s, int tid, double* red) {
         constexpr int TS = 32 * W;
         const int T = P.T;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
         }
         // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
         team_sync<W>();
-        const double logp0 = Model::template eval<NPL, W>(M, data_s, q_s, g_s, lane, red);
+        const double logp0 = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
         team_sync<W>();
         ++n_grad;
         double kin = 0.0;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     q_s[i] = fma(es, var[k] * p[k], q_s[i]);
                 }
                 team_sync<W>();
-                const double logp = Model::template eval<NPL, W>(M, data_s, q_s, g_s, lane, red);
+                const double logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
                 team_sync<W>();
                 ++n_grad;
                 double kk = 0.0;

@@ -15,6 +15,10 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------
 // scalar helpers (same branch structure as the NumPy functions the reference calls)
 // ---------------------------------------------------------------------------------------------
+// log(1 + x) for x >= 0 where the result is ADDED to an O(1) or larger log-density / log-weight: forming 1 + x first costs
+// at most 1.1e-16 ABSOLUTE error, invisible next to the terms it is added to, at half the instructions of log1p().
+__device__ __forceinline__ double log1p_abs(double x) { return log(1.0 + x); }
+
 // numpy.logaddexp (npy_logaddexp): used at hmc/nuts.py:415,376,465
 __device__ __forceinline__ double logaddexp(double x, double y) {
     if (x == y) return x + 0.69314718055994530942;  // log 2
@@ -42,7 +46,7 @@ __device__ __forceinline__ void halfcauchy_log(double z, double x, double beta, 
                                                double& val, double& dz) {
     const double t = x * (1.0 / beta);
     const double u = t * t;
-    val = (0.69314718055994530942 - 1.1447298858494001741 /* log pi */) - log_beta - log1p(u) + z;
+    val = (0.69314718055994530942 - 1.1447298858494001741 /* log pi */) - log_beta - log1p_abs(u) + z;
     dz = 1.0 - 2.0 * u / (1.0 + u);
 }
 

@@ -154,13 +154,17 @@ __host__ __device__ constexpr size_t logistic_smem_bytes() {
     return ((size_t)kLogiChains * (8 * KB + 4) + 2 * (size_t)kLogiRows * (8 * KB + 4)) * sizeof(double) + 64;
 }
 
-template <int KB>
-__global__ void __launch_bounds__(256, 1)
+#ifndef B200_LOGI_MB
+#define B200_LOGI_MB 1  // 8-chain accumulator blocks per warp: 1 -> 16 warps x 8 chains per CTA (126 regs, 4 warps per scheduler:
+                        // 10.8 ms per 512-chain batch), 2 -> 8 warps x 16 chains (212 regs, 12.4 ms)
+#endif
+template <int KB, int MB = B200_LOGI_MB>
+__global__ void __launch_bounds__(32 * (kLogiChains / (8 * MB)), 1)
     logistic_fused_kernel(const double* __restrict__ X /*[Npad][8KB]*/, const uint8_t* __restrict__ y, long long N,
                           const double* __restrict__ Q, long long ldq, int C, int K,
                           double* __restrict__ Gpart /*[gridDim.x][Cpad][8KB]*/, double* __restrict__ lpart /*[gridDim.x][Cpad]*/,
                           int Cpad) {
-    constexpr int KP = 8 * KB, LD = KP + 4;
+    constexpr int KP = 8 * KB, LD = KP + 4, NT = 32 * (kLogiChains / (8 * MB));
     extern __shared__ __align__(16) char smem_raw[];
     double* Qs = reinterpret_cast<double*>(smem_raw);
     double* Xs = Qs + kLogiChains * LD;                       // 2 slabs
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(256, 1)
     const long long n_slabs = (N + kLogiRows - 1) / kLogiRows;
 
     // Q tile (zero rows for chains >= C, zero columns for k >= K)
-    for (int e = tid; e < kLogiChains * KP; e += 256) {
+    for (int e = tid; e < kLogiChains * KP; e += NT) {
         const int r = e / KP, k = e % KP;
         Qs[r * LD + k] = (c_base + r < C && k < K) ? Q[(long long)(c_base + r) * ldq + k] : 0.0;
     }
@@ -187,13 +191,15 @@ __global__ void __launch_bounds__(256, 1)
     long long slab = blockIdx.x;
     if (tid == 0 && slab < n_slabs) issue(slab, 0);
 
-    double G[2][KB][2];
+    double G[MB][KB][2];
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int nb = 0; nb < KB; ++nb) G[mb][nb][0] = G[mb][nb][1] = 0.0;
-    double lp[2] = {0.0, 0.0};
-    const double* qa = Qs + (warp * 16 + g) * LD + t;
+    double lp[MB];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) lp[mb] = 0.0;
+    const double* qa = Qs + (warp * 8 * MB + g) * LD + t;
     const int pg = g ^ ((g >> 2) & 1);  // pi(g)
 
     uint32_t phase[2] = {0, 0};
@@ -204,20 +210,22 @@ __global__ void __launch_bounds__(256, 1)
         phase[buf] ^= 1;
         const double* xs = Xs + buf * kLogiRows * LD;
         // ---- GEMM 1: etaT[16 chains][32 rows]; B fragment = X[8 nb + pi(g)][k0 + t]
-        double E[2][4][2];
+        double E[MB][4][2];
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) E[mb][nb][0] = E[mb][nb][1] = 0.0;
         const double* xb = xs + pg * LD + t;
 #pragma unroll 4
         for (int ks = 0; ks < KP; ks += 4) {
-            const double a0 = qa[ks], a1 = qa[8 * LD + ks];
+            double a[MB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) a[mb] = qa[mb * 8 * LD + ks];
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 const double b = xb[nb * 8 * LD + ks];
-                dmma884(E[0][nb][0], E[0][nb][1], a0, b);
-                dmma884(E[1][nb][0], E[1][nb][1], a1, b);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) dmma884(E[mb][nb][0], E[mb][nb][1], a[mb], b);
             }
         }
         // ---- epilogue: accumulator column n = 2t + s is row  8 nb + pi(2t + s)  of the slab
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(256, 1)
                 const bool live = row < N;
                 const double yi = live ? (double)y[row] : 0.0;
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+                for (int mb = 0; mb < MB; ++mb) {
                     const double x = E[mb][nb][s];
                     const double ex = exp(-fabs(x));
                     const double rr = 1.0 / (1.0 + ex);
@@ -252,8 +260,8 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
                     const double b = xr[kb * 8];
-                    dmma884(G[0][kb][0], G[0][kb][1], E[0][nb][s], b);
-                    dmma884(G[1][kb][0], G[1][kb][1], E[1][nb][s], b);
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) dmma884(G[mb][kb][0], G[mb][kb][1], E[mb][nb][s], b);
                 }
             }
         }
@@ -261,8 +269,8 @@ __global__ void __launch_bounds__(256, 1)
     }
     // ---- partial results of this row-CTA
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
-        const int c = c_base + warp * 16 + mb * 8 + g;
+    for (int mb = 0; mb < MB; ++mb) {
+        const int c = c_base + warp * 8 * MB + mb * 8 + g;
         double l = lp[mb];
         l += __shfl_xor_sync(B200_FULL_MASK, l, 1);
         l += __shfl_xor_sync(B200_FULL_MASK, l, 2);

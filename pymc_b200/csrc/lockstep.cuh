@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 const double dlw = S.c_logw - t_logw;
                 const double e_w = exp(-fabs(dlw));
                 const double logw = (dlw == 0.0) ? S.c_logw + 0.69314718055994530942
-                                                 : (isnan(dlw) ? S.c_logw + t_logw : fmax(S.c_logw, t_logw) + log1p(e_w));
+                                                 : (isnan(dlw) ? S.c_logw + t_logw : fmax(S.c_logw, t_logw) + log1p_abs(e_w));
                 const double u = rng.next_double();
                 if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                     const double* t_pq = LVL(h, 5); const double* t_pqg = LVL(h, 6); const double* t_pqw = LVL(h, 7);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                         S.m_pe = S.c_pe; S.m_plogp = S.c_plogp; S.m_pidx = S.c_pidx;
                     }
                     S.m_logw = (dlw == 0.0) ? S.c_logw + 0.69314718055994530942
-                                            : (isnan(dlw) ? S.c_logw + S.m_logw : fmax(S.c_logw, S.m_logw) + log1p(e_w));
+                                            : (isnan(dlw) ? S.c_logw + S.m_logw : fmax(S.c_logw, S.m_logw) + log1p_abs(e_w));
                 }
                 // U-turn checks on the whole tree (nuts.py:376-390)
                 {

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     const double dlw = c_logw - t_logw;
                     const double e_w = exp(-fabs(dlw));
                     const double logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
-                                                     : (isnan(dlw) ? c_logw + t_logw : fmax(c_logw, t_logw) + log1p(e_w));
+                                                     : (isnan(dlw) ? c_logw + t_logw : fmax(c_logw, t_logw) + log1p_abs(e_w));
                     const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
                     if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                         const double* t_pq = lvl(h, 3);
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
                 }
                 m_logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
-                                      : (isnan(dlw) ? c_logw + m_logw : fmax(c_logw, m_logw) + log1p(e_w));
+                                      : (isnan(dlw) ? c_logw + m_logw : fmax(c_logw, m_logw) + log1p_abs(e_w));
             }
             // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
             {

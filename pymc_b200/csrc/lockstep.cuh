@@ -377,9 +377,14 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             }
         }
         S.E0 = 0.5 * team_sum<W>(kin, lane, red) - S.cur_logp;
-        if (!isfinite(S.E0)) {  // "Bad initial energy" (base_hmc.py:205-224)
+        if (!isfinite(S.E0)) {  // "Bad initial energy" (base_hmc.py:205-224): freeze; the iterations that never ran are NaN
             S.bad_at = S.it;
             S.phase = 2;
+            for (int t = S.it; t < Ttot; ++t) {
+                if (!(P.store_warmup || t >= P.tune)) continue;
+                const int t_o = P.store_warmup ? t : t - P.tune;
+                for (int i = lane; i < n; i += TS) P.draws_out[((long long)chain * T_out + t_o) * n + i] = nan("");
+            }
         } else {
             S.eps = exp(adapting ? S.log_step : S.log_bar);
             S.maxd = (tuning && S.it < 200) ? P.early_td : P.max_td;

@@ -518,6 +518,18 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
         team_sync<W>();
     }
 
+    // ---- a frozen chain ("Bad initial energy"): the iterations that never ran are NaN in the output --------------
+    if (bad_at >= 0) {
+        for (int t = bad_at; t < Ttot; ++t) {
+            if (!(P.store_warmup || t >= P.tune)) continue;
+            const int t_out = P.store_warmup ? t : t - P.tune;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                if (i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = nan("");
+            }
+        }
+    }
     // ---- end of run: hand the streams and adaptation results back --------------------------------------
     if (lane == 0) {
         b200_pcg64 r;

@@ -164,7 +164,7 @@ class CompiledModel:
             q0_b, var0_b, mean0_b, z_b = to_dev(q0), to_dev(var0), to_dev(mean0), to_dev(z)
             eps0_b = to_dev(eps0)
             rng_b = torch.as_tensor(rng_states.view(np.uint64).reshape(Cn, 4).view(np.int64), device=dev)
-            draws_b = torch.full((Cn, T, self.n), float("nan"), dtype=torch.float64, device=dev)
+            draws_b = torch.empty((Cn, T, self.n), dtype=torch.float64, device=dev)  # frozen chains: NaN-filled by the kernel
             tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
             mk = lambda shape, dt: torch.zeros(shape, dtype=tdt[dt], device=dev)  # noqa: E731
         else:

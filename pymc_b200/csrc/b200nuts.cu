@@ -491,11 +491,8 @@ static int launch_gemm(cudaStream_t st, const double* Q, long long ldq, int C, c
     constexpr int NST = 3;
     const size_t smem = NST * gemm_stage_doubles<WM, NB>() * sizeof(double);
     auto kern = gemm_nt_dmma_kernel<WM, NB, NST>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per call: the attribute belongs to the (function, device) pair and a process may own handles on several devices
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((Nout + 8 * NB - 1) / (8 * NB), (C + 16 * WM - 1) / (16 * WM));
     kern<<<grid, 32 * WM, smem, st>>>(Q, ldq, C, M, ldm, Nout, K, alpha, D, ldd);
     CU(cudaGetLastError());
@@ -539,11 +536,7 @@ template <int KB>
 static int launch_logistic(const b200_model* m, int C, const double* Q, long long ldq, BatchScratch& bs, cudaStream_t st) {
     auto kern = logistic_fused_kernel<KB>;
     const size_t smem = logistic_smem_bytes<KB>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(bs.gx, bs.cpad / kLogiChains), 32 * (kLogiChains / (8 * B200_LOGI_MB)), smem, st>>>(m->X, m->y8, m->n_rows, Q, ldq, C, m->n, bs.gpart.as<double>(),
                                                                bs.lpart.as<double>(), bs.cpad);
     CU(cudaGetLastError());

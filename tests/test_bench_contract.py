@@ -1,0 +1,41 @@
+"""CPU: bench.py's contract pieces that need no GPU -- workload table, CPU-sample planning, and the reference arm's
+JSON line (run as a subprocess on a tiny sample)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_workload_table_covers_the_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+    from pymc_b200 import models
+
+    assert set(bench.WORKLOADS) == {"radon", "logistic", "stochvol", "mvgauss"}
+    for name, wl in bench.WORKLOADS.items():
+        assert wl["builder"] in models.BUILDERS and wl["bound"] in ("hbm", "tensor") and wl["scaling"] in ("weak", "strong")
+        assert wl["per_eval"] > 0 and wl["chains"] > 0
+    # Radon algorithmic bytes per grad-eval = 919 (8+8+4) + 7 * 175 * 8
+    assert bench.WORKLOADS["radon"]["per_eval"] == 28180
+    assert bench.WORKLOADS["radon"]["chains"] == 2048 and bench.WORKLOADS["mvgauss"]["scaling"] == "strong"
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-chains", "2", "--tune", "6", "--draws", "4"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "leapfrog_grad_evals_per_sec" and line["unit"] == "grad-evals/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["workload"].startswith("radon_hierarchical")
+
+
+def test_reference_arm_is_silent_on_nonzero_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -41,7 +41,8 @@ def test_fixed_step_chains_reproduce_golden(golden, name):
         assert np.max(np.abs(st["energy"] - d["stat_energy"][c])) <= 1e-9
 
 
-@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_small_adapt", "radon_adapt", "stochvol_small_adapt"])
+@pytest.mark.parametrize("name", ["eight_schools_adapt", "radon_small_adapt", "radon_adapt", "stochvol_small_adapt",
+                                  "logistic_small_adapt"])
 def test_single_draw_replay_of_adaptive_golden(golden, name):
     d = golden(name)
     spec = SPEC_OF[name]()
@@ -78,6 +79,21 @@ def test_adaptation_prefix_reproduces_golden(golden, name):
     o = nuts_numpy.Oracle(f, mass, step_scale=float(d["step_scale"]))
     o.rng = _gen_from_state(d["pre_rng"][0][0])
     T = 120
+    qs, st = o.run(d["q0"][0], T, 0, z=d["z"][0][:T])
+    assert np.array_equal(st["tree_size"], d["stat_tree_size"][0][:T])
+    assert np.max(np.abs(st["step_size"] - d["stat_step_size"][0][:T]) / d["stat_step_size"][0][:T]) <= 1e-9
+    assert np.max(np.abs(qs - d["draws_q"][0][:T])) <= 1e-7
+
+
+def test_dense_mass_step_adaptation_prefix_reproduces_golden(golden):
+    """QuadPotentialFull (fixed dense covariance) + dual averaging: the first iterations of the reference run."""
+    name = "mvgauss_dense_stepadapt"
+    d = golden(name)
+    spec = SPEC_OF[name]()
+    f = logp_numpy.make_logp(spec)
+    o = nuts_numpy.Oracle(f, nuts_numpy.DenseMass(spec.data["cov"]))
+    o.rng = _gen_from_state(d["pre_rng"][0][0])
+    T = 40
     qs, st = o.run(d["q0"][0], T, 0, z=d["z"][0][:T])
     assert np.array_equal(st["tree_size"], d["stat_tree_size"][0][:T])
     assert np.max(np.abs(st["step_size"] - d["stat_step_size"][0][:T]) / d["stat_step_size"][0][:T]) <= 1e-9

@@ -66,7 +66,21 @@ struct b200_model {
     const uint8_t* y8 = nullptr;    // LOGISTIC: y[N]
     long long n_rows = 0;
     int KP = 0;
+    // per-chain tree scratch of the persistent kernel, kept between runs (cudaMalloc/cudaFree of 100+ MB per call costs
+    // tens of milliseconds of host time on the end-to-end path)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaError_t ensure_scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return cudaSuccess;
+        if (scratch) cudaFree(scratch);
+        scratch = nullptr;
+        scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&scratch, bytes);
+        if (e == cudaSuccess) scratch_bytes = bytes;
+        return e;
+    }
     ~b200_model() {
+        if (scratch) cudaFree(scratch);
         for (void* p : owned) cudaFree(p);
     }
 };
@@ -670,7 +684,7 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
 // b200_nuts_run
 // ------------------------------------------------------------------------------------------------
 struct NutsLaunch {
-    const b200_model* m; NutsDev P; cudaStream_t st;
+    b200_model* m; NutsDev P; cudaStream_t st;
     template <class Model, int NPL, int W>
     int operator()(const typename Model::Params& MP) {
         constexpr int NP = 32 * W * NPL;
@@ -687,10 +701,9 @@ struct NutsLaunch {
         }
         if (smem > 227 * 1024) return fail("nuts: shared memory request %zu B exceeds 227 KB", smem);
         P.hot_levels = hot;
-        DevBuf scratch;
         P.scratch_stride = nuts_scratch_doubles(NP, P.max_td);
-        CU(scratch.alloc((size_t)P.C * P.scratch_stride * sizeof(double)));
-        P.scratch = scratch.as<double>();
+        CU(m->ensure_scratch((size_t)P.C * P.scratch_stride * sizeof(double)));
+        P.scratch = static_cast<double*>(m->scratch);
         auto kern = nuts_warp_kernel<Model, NPL, W, SUBS>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = (P.C + wpb - 1) / wpb;
@@ -748,7 +761,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     if (stats) {
 #define B200_ST(i, field, type)                                                              \
     if (stats->field) {                                                                      \
-        if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st)) return -1; \
+        if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st, /*direct=*/true)) return -1; \
         ds.field = (type*)st_arr[i].ptr();                                                   \
     }
         B200_ST(0, depth, int32_t) B200_ST(1, tree_size, int32_t) B200_ST(2, index_in_trajectory, int32_t)
@@ -759,19 +772,19 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     }
     if (summary) {
         if (summary->grad_evals) {
-            if (stage_in(sm_arr[0], summary->grad_evals, (size_t)C * sizeof(int64_t), mem, false, true, st)) return -1;
+            if (stage_in(sm_arr[0], summary->grad_evals, (size_t)C * sizeof(int64_t), mem, false, true, st, true)) return -1;
             dsum.grad_evals = (int64_t*)sm_arr[0].ptr();
         }
         if (summary->bad_energy_at) {
-            if (stage_in(sm_arr[1], summary->bad_energy_at, (size_t)C * sizeof(int32_t), mem, false, true, st)) return -1;
+            if (stage_in(sm_arr[1], summary->bad_energy_at, (size_t)C * sizeof(int32_t), mem, false, true, st, true)) return -1;
             dsum.bad_energy_at = (int32_t*)sm_arr[1].ptr();
         }
         if (summary->final_step_size) {
-            if (stage_in(sm_arr[2], summary->final_step_size, (size_t)C * sizeof(double), mem, false, true, st)) return -1;
+            if (stage_in(sm_arr[2], summary->final_step_size, (size_t)C * sizeof(double), mem, false, true, st, true)) return -1;
             dsum.final_step_size = (double*)sm_arr[2].ptr();
         }
         if (summary->final_var) {
-            if (stage_in(sm_arr[3], summary->final_var, vb, mem, false, true, st)) return -1;
+            if (stage_in(sm_arr[3], summary->final_var, vb, mem, false, true, st, true)) return -1;
             dsum.final_var = (double*)sm_arr[3].ptr();
         }
     }

@@ -13,7 +13,7 @@ def __getattr__(name):  # lazy: importing the package must not require the built
         from . import sampling
 
         return getattr(sampling, name)
-    if name in ("B200LogpDlogp", "from_pymc"):
+    if name in ("B200LogpDlogp", "B200NUTS", "from_pymc"):
         from . import step
 
         return getattr(step, name)

@@ -31,6 +31,141 @@ class B200LogpDlogp:
         return self._pytensor_function(q)
 
 
+class B200NUTS:
+    """Seam B3: a step-method object with the ``BlockedStep`` / ``NUTS`` protocol that
+    ``pm.sample(step=...)``'s chain loop drives (``_iter_sample``, pymc/sampling/mcmc.py:1503-1578):
+
+        step.setup_chain(rng, tune, draws); step.tune = bool(tune); step.reset_tuning()
+        for i in range(tune + draws):
+            if i == tune: step.stop_tuning()
+            point, stats = step.step(point)
+
+    One chain per object, like the reference.  ``setup_chain`` announces ``tune`` and ``draws``, so the WHOLE chain runs
+    on the device inside the first ``step`` call (one ``b200_nuts_run``) and the following calls hand its iterations out
+    one by one.  Streams are derived as the reference derives them (``self.rng = rng``; the potential draws its momentum
+    normals from ``rng.spawn(1)[0]``, hmc/base_hmc.py:300-302), so with ``momentum="numpy"`` a chain equals the chain the
+    reference's own ``NUTS`` produces from the same generator, and ``rng`` is left where the reference would leave it.
+    Defaults follow ``BaseHMC.__init__`` (hmc/base_hmc.py:82-169): ``QuadPotentialDiagAdapt(n, zeros, ones, 10)``.
+    """
+
+    name = "nuts"
+    default_blocked = True
+    # NUTS.stats_dtypes_shapes (hmc/nuts.py:110-130); "warning" carries None here
+    stats_dtypes_shapes = {
+        "depth": (np.int64, []), "step_size": (np.float64, []), "mean_tree_accept": (np.float64, []),
+        "step_size_bar": (np.float64, []), "tree_size": (np.float64, []), "diverging": (bool, []),
+        "divergences": (int, []), "energy_error": (np.float64, []), "energy": (np.float64, []),
+        "max_energy_error": (np.float64, []), "model_logp": (np.float64, []), "process_time_diff": (np.float64, []),
+        "perf_counter_diff": (np.float64, []), "perf_counter_start": (np.float64, []), "largest_eigval": (np.float64, []),
+        "smallest_eigval": (np.float64, []), "index_in_trajectory": (np.int64, []), "reached_max_treedepth": (bool, []),
+        "warning": (object, None),
+    }
+
+    def __init__(self, model, *, max_treedepth=10, early_max_treedepth=8, target_accept=0.8, step_scale=0.25, gamma=0.05,
+                 k=0.75, t0=10, Emax=1000, adapt_step_size=True, potential_mean=None, potential_var=None,
+                 potential_weight=10.0, momentum="numpy", rng=None):
+        self._cm = model if hasattr(model, "nuts_run") else CompiledModel(model)
+        self.spec = self._cm.spec
+        self.vars = list(self.spec.vars)
+        n = self.spec.n
+        self._kw = dict(max_treedepth=max_treedepth, early_max_treedepth=early_max_treedepth, target_accept=target_accept,
+                        step_scale=step_scale, gamma=gamma, k=k, t0=t0, Emax=Emax, adapt_step_size=adapt_step_size,
+                        mass_initial_weight=potential_weight)
+        self._mean0 = np.zeros(n) if potential_mean is None else np.asarray(potential_mean, dtype=np.float64).reshape(n)
+        self._var0 = np.ones(n) if potential_var is None else np.asarray(potential_var, dtype=np.float64).reshape(n)
+        if momentum not in ("numpy", "device"):
+            raise ValueError("momentum must be 'numpy' or 'device'")
+        self._momentum = momentum
+        self.rng = np.random.default_rng(rng)
+        self.tune = True
+        self.iter_count = 0
+        self.divergences = 0
+        self._tune_n = self._draws_n = None
+        self._res = None
+
+    # ---- BlockedStep protocol (step_methods/compound.py:132-250) -------------------------------------------------
+    @staticmethod
+    def competence(var, has_grad):
+        return 3 if has_grad and np.issubdtype(np.dtype(getattr(var, "dtype", "float64")), np.floating) else 0
+
+    def setup_chain(self, rng, tune: int, draws: int) -> None:
+        self.rng = rng
+        self._tune_n, self._draws_n = int(tune), int(draws)
+        self._res = None
+
+    def reset_tuning(self, start=None):
+        self.iter_count = 0
+        self.divergences = 0
+        self.tune = True
+        self._res = None
+
+    def stop_tuning(self):
+        if self._tune_n is not None and self.iter_count != self._tune_n and self._res is not None:
+            raise RuntimeError(f"stop_tuning() at iteration {self.iter_count}, but setup_chain announced tune={self._tune_n}: "
+                               "the chain already ran on the device with that schedule")
+        self.tune = False
+
+    def _ravel(self, point):
+        return np.concatenate([np.ravel(np.asarray(point[v.name], dtype=np.float64)) for v in self.vars])
+
+    def _run_chain(self, q0):
+        from . import rng as brng
+
+        if self._tune_n is None:
+            raise RuntimeError("setup_chain(rng, tune, draws) must be called before step(): the chain runs as one device launch")
+        T = self._tune_n + self._draws_n
+        tune = self._tune_n if self.tune else 0  # a chain whose tuning was stopped before its first step samples only
+        states = brng.pack_pcg64([self.rng])
+        z, seed = None, 0
+        if self._momentum == "numpy":
+            z = brng.momentum_noise([self.rng.spawn(1)[0]], T, self.spec.n)
+        else:
+            seed = int(self.rng.spawn(1)[0].integers(2**63))
+        self._res = self._cm.nuts_run(q0[None, :], states, tune=tune, draws=T - tune, z=z, philox_seed=seed, store_warmup=True,
+                                      mass="diag_adapt", mean0=self._mean0[None, :], var0=self._var0[None, :], **self._kw)
+        brng.unpack_pcg64(states, [self.rng])  # the host generator continues where the device stopped
+        if int(self._res.summary["bad_energy_at"][0]) >= 0:
+            from .sampling import SamplingError
+
+            raise SamplingError(f"Bad initial energy at iteration {int(self._res.summary['bad_energy_at'][0])}")
+
+    def step(self, point):
+        import time
+
+        t0 = time.perf_counter()
+        if self._res is None:
+            self._run_chain(self._ravel(point))
+        i = self.iter_count
+        if i >= np.asarray(self._res.draws).shape[1]:
+            raise RuntimeError("step() called more often than setup_chain announced (tune + draws)")
+        q = np.asarray(self._res.draws[0, i])
+        st = {k: v[0, i] for k, v in self._res.stats.items()}
+        diverging = bool(st["diverging"])
+        if not self.tune:
+            self.divergences += diverging
+        self.iter_count += 1
+        new_point = dict(point)
+        for v in self.vars:
+            new_point[v.name] = q[v.offset : v.offset + v.size].reshape(np.shape(point[v.name])).copy()
+        t1 = time.perf_counter()
+        stats = {
+            "depth": int(st["depth"]), "step_size": float(st["step_size"]),
+            "mean_tree_accept": float(st["mean_tree_accept"]), "step_size_bar": float(st["step_size_bar"]),
+            "tree_size": float(st["tree_size"]), "diverging": diverging, "divergences": self.divergences,
+            "energy_error": float(st["energy_error"]), "energy": float(st["energy"]),
+            "max_energy_error": float(st["max_energy_error"]), "model_logp": float(st["model_logp"]),
+            "process_time_diff": t1 - t0, "perf_counter_diff": t1 - t0, "perf_counter_start": t0,
+            "largest_eigval": np.nan, "smallest_eigval": np.nan,  # QuadPotential.stats() (quadpotential.py:177-178)
+            "index_in_trajectory": int(st["index_in_trajectory"]), "reached_max_treedepth": bool(st["reached_max_treedepth"]),
+            "warning": None,
+        }
+        return new_point, [stats]
+
+    @property
+    def sampling_state(self):
+        return {"iter_count": self.iter_count, "tune": self.tune, "divergences": self.divergences}
+
+
 def from_pymc(model):
     """Lower a ``pm.Model`` to a ``ModelSpec``.  Not implemented this round: PyMC/PyTensor are
     not importable in this image, so the lowering cannot be exercised; use ``pymc_b200.models`` specs."""

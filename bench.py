@@ -128,7 +128,7 @@ def _cpu_chain(job):
     o.setup_chain(np.random.default_rng(seed + 1))
     t0 = time.perf_counter()
     qs, st = o.run(q0, tune, draws)
-    return int(st["tree_size"].sum()), time.perf_counter() - t0, qs[tune:, :4]
+    return int(st["tree_size"].sum()), time.perf_counter() - t0, qs[tune:, :4096]
 
 
 def cpu_run(chains, tune, draws, seed0, pool, workload="radon", threads=1):
@@ -137,6 +137,20 @@ def cpu_run(chains, tune, draws, seed0, pool, workload="radon", threads=1):
     wall = time.perf_counter() - t0
     evals = sum(o[0] for o in out)
     return evals, wall, np.stack([o[2] for o in out])
+
+
+def cpu_ess(qs, wall):
+    """ESS/s of a CPU sample: rank-normalised bulk ESS (min over parameters) of the post-warm-up draws / wall time of the
+    whole sample (warm-up included) -- the same estimator and convention as the GPU line's `ess`."""
+    from pymc_b200 import diagnostics
+
+    if qs.shape[0] < 2 or qs.shape[1] < 8:
+        return None
+    try:
+        e = float(np.nanmin(diagnostics.ess_bulk(qs)))
+    except Exception:  # a diagnostic must never take the bench line down
+        return None
+    return {"min_bulk_ess": e, "ess_per_sec": e / wall, "chains": int(qs.shape[0]), "draws": int(qs.shape[1])}
 
 
 def host_cores():
@@ -168,11 +182,12 @@ def reference_arm(args):
     with mp.get_context("spawn").Pool(procs) as pool:
         for _ in range(1 if args.warmup else 0):  # imports, model build (and BLAS warm-up) in every worker
             cpu_run(procs, 2, 1, 999, pool, args.workload, threads)
-        evals, wall = 0, 0.0
+        evals, wall, ess = 0, 0.0, None
         for s in range(args.steps):
-            e, w, _ = cpu_run(chains, tune, draws, 1000 * (s + 1), pool, args.workload, threads)
+            e, w, qs = cpu_run(chains, tune, draws, 1000 * (s + 1), pool, args.workload, threads)
             evals += e
             wall += w
+            ess = cpu_ess(qs, w)
     value = evals / wall
     sample = (f"{chains} chains x ({tune} tune + {draws} draws) of the same {args.workload} model per step, {procs} processes x "
               f"{threads} BLAS threads")
@@ -182,7 +197,7 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, (args.chains_per_gpu or args.wl["chains"])), **args.wl["desc"],
                    "note": "bounded CPU sample of the same workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ess": ess},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -419,7 +434,7 @@ def b200_arm(args):
             e, w, qs = cpu_run(chains, ct, cd, 12345, pool, args.workload, threads)
         cpu = {"value": e / w, "unit": UNIT, "cores": procs * threads, "kind": "port",
                "sample": f"{chains} chains x ({ct} tune + {cd} draws) of the same {args.workload} model, {procs} processes x "
-                         f"{threads} BLAS threads", "wall_s": w}
+                         f"{threads} BLAS threads", "wall_s": w, "ess": cpu_ess(qs, w)}
 
     if rank == 0:
         line = {

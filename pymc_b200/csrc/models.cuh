@@ -16,6 +16,11 @@
 
 namespace b200 {
 
+#ifndef B200_RADON_SMALL_UNROLL
+#define B200_RADON_SMALL_UNROLL 1  // untested candidate: 2 (ping-pong of the prefetch registers, no register moves)
+#endif
+constexpr int kRadonSmallUnroll = B200_RADON_SMALL_UNROLL;
+
 // ------------------------------------------------------------------------------------------------
 // x ~ Normal(0,1)^n  (test model; Normal.logp distributions/continuous.py:526-527)
 // ------------------------------------------------------------------------------------------------
@@ -168,7 +173,7 @@ struct RadonModel {
             double Ga0 = 0.0, Gb0 = 0.0, S20 = 0.0, Ga1 = 0.0, Gb1 = 0.0, S21 = 0.0;
             // SMALL: no unrolling inside the persistent NUTS kernel, whose hot code must stay inside the instruction cache
             // (measured: 511 vs 562 ms per bench step); the stand-alone leapfrog/logp kernels unroll (540 vs 393 M evals/s)
-#pragma unroll(SMALL ? 1 : 4)
+#pragma unroll(SMALL ? kRadonSmallUnroll : 4)
             for (int b = 0, kb = 0; b < nblk; ++b, kb += 4) {
                 ptr += 128;
                 const double2 n0 = ptr[0], n1 = ptr[32], n2 = ptr[64], n3 = ptr[96];

@@ -24,7 +24,7 @@ def test_workload_table_covers_the_baseline_configs():
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-chains", "2", "--tune", "6", "--draws", "4"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--cpu-chains", "2", "--tune", "6", "--draws", "8"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "leapfrog_grad_evals_per_sec" and line["unit"] == "grad-evals/s"
@@ -32,6 +32,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["config"]["workload"].startswith("radon_hierarchical")
+    ess = line["cpu_baseline"]["ess"]  # ESS/s of the CPU sample, same estimator as the GPU line
+    assert ess["chains"] == 2 and ess["draws"] == 8 and ess["ess_per_sec"] > 0
 
 
 def test_reference_arm_is_silent_on_nonzero_ranks():

@@ -124,7 +124,7 @@ def sample_b200_nuts(
         raise TypeError("model is required (a pymc_b200.models.ModelSpec or a CompiledModel)")
     if chain_method not in ("vectorized", "parallel"):
         raise ValueError("chain_method must be 'vectorized' or 'parallel'")
-    cm = model if isinstance(model, CompiledModel) else CompiledModel(model)
+    cm = model if hasattr(model, "nuts_run") else CompiledModel(model)  # a CompiledModel (or an object with its interface)
     spec = cm.spec
     nk = dict(nuts_kwargs or {})
     nk.setdefault("target_accept", target_accept)

@@ -106,3 +106,58 @@ def discrete_equal(st, d, chain):
             continue
         ok &= np.asarray(st[k]).astype(np.int64) == np.asarray(d["stat_" + k][chain]).astype(np.int64)
     return ok
+
+
+class OracleEngine:
+    """CPU stand-in for ``pymc_b200.engine.CompiledModel`` in host-logic tests: same ``nuts_run`` / ``logp_dlogp``
+    interface, every chain run through oracle/nuts_numpy.py (bit-identical to the reference).  Lets the seams above the
+    C ABI (step method, whole-run sampler, chain sharding over torch.distributed) be tested without a GPU."""
+
+    def __init__(self, spec):
+        from oracle import logp_numpy
+
+        self.spec, self.n = spec, spec.n
+        self.f = logp_numpy.make_logp(spec)
+
+    def logp_dlogp(self, q):
+        q = np.asarray(q, dtype=np.float64).reshape(-1, self.n)
+        out = [self.f(x) for x in q]
+        return np.array([o[0] for o in out]), np.array([o[1] for o in out])
+
+    def nuts_run(self, q0, rng_states, *, tune, draws, z=None, mean0=None, var0=None, mass="diag_adapt", store_warmup=True,
+                 philox_seed=0, mass_initial_weight=10.0, step_scale=0.25, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,
+                 Emax=1000.0, adapt_step_size=True, max_treedepth=10, early_max_treedepth=8, chain_offset=0, **unused):
+        from oracle import nuts_numpy
+        from pymc_b200.engine import NutsResult
+
+        assert mass == "diag_adapt" and z is not None, "the stand-in draws momentum from the host stream only"
+        q0 = np.asarray(q0, dtype=np.float64).reshape(-1, self.n)
+        C, T = q0.shape[0], tune + draws
+        qs_all, st_all = [], []
+        for c in range(C):
+            v0 = np.ones(self.n) if var0 is None else np.asarray(var0)[c]
+            m0 = np.zeros(self.n) if mean0 is None else np.asarray(mean0)[c]
+            m = nuts_numpy.DiagMass(v0, adapt=True, initial_mean=m0.copy(), initial_weight=mass_initial_weight)
+            o = nuts_numpy.Oracle(self.f, m, step_scale=step_scale, adapt_step_size=adapt_step_size, target_accept=target_accept,
+                                  gamma=gamma, k=k, t0=t0, Emax=Emax, max_treedepth=max_treedepth,
+                                  early_max_treedepth=early_max_treedepth)
+            g = np.random.default_rng(0)
+            st = g.bit_generator.state
+            rec = rng_states[c]
+            st["state"]["state"] = (int(rec["state_hi"]) << 64) | int(rec["state_lo"])
+            st["state"]["inc"] = (int(rec["inc_hi"]) << 64) | int(rec["inc_lo"])
+            st["has_uint32"], st["uinteger"] = 0, 0
+            g.bit_generator.state = st
+            o.rng = g
+            qs, stats = o.run(q0[c], tune, draws, z=np.asarray(z)[c])
+            s = g.bit_generator.state["state"]
+            rng_states[c] = (s["state"] >> 64, s["state"] & (2**64 - 1), s["inc"] >> 64, s["inc"] & (2**64 - 1))
+            w = 0 if store_warmup else tune
+            qs_all.append(qs[w:])
+            st_all.append({k_: np.asarray(v)[w:] for k_, v in stats.items()})
+        dt = {"depth": np.int32, "tree_size": np.int32, "index_in_trajectory": np.int32, "diverging": np.uint8,
+              "reached_max_treedepth": np.uint8}
+        names = [nm for nm, _ in _lib.STAT_FIELDS]  # exactly the arrays b200_stats carries
+        stats = {k_: np.stack([s[k_] for s in st_all]).astype(dt.get(k_, np.float64)) for k_ in names}
+        return NutsResult(draws=np.stack(qs_all), stats=stats, summary={"bad_energy_at": np.full(C, -1, dtype=np.int32)},
+                          kernel_ms=0.0, launches=0, tune=tune, n_draws=draws, store_warmup=store_warmup)

@@ -1,0 +1,92 @@
+"""CPU: seam B4 (``sample_b200_nuts``) above the C ABI, with the device engine replaced by the oracle-backed stand-in:
+stream derivation per chain, init (jitter + mean start point), result packaging and names, reproducibility, and chain
+sharding over torch.distributed (gloo, world_size 2) giving the same posterior as a single process."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from b200_helpers import OracleEngine
+from pymc_b200 import models, sampling
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(chains=3, seed=11, **kw):
+    spec = models.eight_schools()
+    return sampling.sample_b200_nuts(20, tune=40, chains=chains, random_seed=seed, model=OracleEngine(spec), momentum="numpy",
+                                     keep_untransformed=True, **kw)
+
+
+def test_whole_run_sampler_conventions_and_reproducibility():
+    a, b = run(), run()
+    assert np.array_equal(a.unconstrained, b.unconstrained)  # same seed => identical posterior (test_mcmc_external.py:83)
+    assert set(a.posterior) == {"mu", "tau", "theta_t"} and a.posterior["theta_t"].shape == (3, 20, 8)
+    assert {"diverging", "energy", "tree_depth", "n_steps", "acceptance_rate", "lp", "step_size"} <= set(a.sample_stats)
+    assert a.sample_stats["diverging"].dtype == bool and a.sample_stats["n_steps"].shape == (3, 20)
+    assert a.attrs["tuning_steps"] == 40 and a.attrs["inference_library"] == "pymc_b200" and "sampling_time" in a.attrs
+    assert np.all(a.posterior["tau"] > 0) and np.allclose(np.log(a.posterior["tau"]), a.unconstrained[..., 1])
+    c = run(seed=12)
+    assert not np.array_equal(a.unconstrained, c.unconstrained)
+    w = run(discard_tuned_samples=False)
+    assert w.warmup_posterior["mu"].shape == (3, 40) and np.array_equal(w.unconstrained, a.unconstrained)
+    only = run(var_names=["mu"])
+    assert set(only.posterior) == {"mu"}
+
+
+def test_chains_are_the_reference_chains_for_their_streams():
+    """Chain c of the whole-run sampler == the oracle (== the reference) run on chain c's own streams and start."""
+    from oracle import logp_numpy, nuts_numpy
+    from pymc_b200 import rng as brng
+
+    spec = models.eight_schools()
+    chains, seed, tune, draws = 3, 5, 30, 10
+    res = sampling.sample_b200_nuts(draws, tune=tune, chains=chains, random_seed=seed, model=OracleEngine(spec), momentum="numpy",
+                                    keep_untransformed=True)
+    step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(seed, chains)
+    q0 = sampling.initial_points(spec, chains, jitter_seeds)
+    f = logp_numpy.make_logp(spec)
+    for c in range(chains):
+        m = nuts_numpy.DiagMass(np.ones(spec.n), adapt=True, initial_mean=q0.mean(axis=0), initial_weight=10)  # mcmc.py:1890-1894
+        o = nuts_numpy.Oracle(f, m)
+        o.rng, o.mass.rng = step_rngs[c], pot_rngs[c]
+        qs, _ = o.run(q0[c], tune, draws)
+        assert np.array_equal(qs[tune:], res.unconstrained[c])
+
+
+WORKER = textwrap.dedent(
+    """
+    import os, sys
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np, torch.distributed as dist
+    from b200_helpers import OracleEngine
+    from pymc_b200 import models, sampling
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    spec = models.eight_schools()
+    res = sampling.sample_b200_nuts(12, tune=25, chains=5, random_seed=3, model=OracleEngine(spec), momentum="numpy",
+                                    keep_untransformed=True)
+    np.save(sys.argv[2], res.unconstrained)
+    assert res.sample_stats["n_steps"].shape == (5, 12)
+    dist.destroy_process_group()
+    print("ok")
+    """
+)
+
+
+def test_sharded_run_world_size_2_gloo_equals_single_process(tmp_path):
+    port = 29700 + (os.getpid() % 200)
+    script = tmp_path / "w.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    outs = [str(tmp_path / f"r{r}.npy") for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), outs[r]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+    spec = models.eight_schools()
+    single = sampling.sample_b200_nuts(12, tune=25, chains=5, random_seed=3, model=OracleEngine(spec), momentum="numpy",
+                                       keep_untransformed=True)
+    for o in outs:  # every rank holds all chains after the gather, identical to the unsharded run
+        assert np.array_equal(np.load(o), single.unconstrained)

@@ -7,41 +7,12 @@ CPU: the device engine is replaced by a stand-in with the ``CompiledModel.nuts_r
 import numpy as np
 import pytest
 
-from oracle import logp_numpy, nuts_numpy, ref_loader
+from b200_helpers import OracleEngine
+from oracle import logp_numpy, ref_loader
 from pymc_b200 import models
-from pymc_b200.engine import NutsResult
 from pymc_b200.step import B200NUTS
 
 needs_reference = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present")
-
-
-class OracleEngine:
-    """CompiledModel stand-in: one chain through oracle/nuts_numpy.py with the arguments B200NUTS passes."""
-
-    def __init__(self, spec):
-        self.spec, self.n = spec, spec.n
-        self.f = logp_numpy.make_logp(spec)
-
-    def nuts_run(self, q0, rng_states, *, tune, draws, z, mean0, var0, mass, store_warmup, philox_seed, mass_initial_weight,
-                 step_scale, target_accept, gamma, k, t0, Emax, adapt_step_size, max_treedepth, early_max_treedepth):
-        assert mass == "diag_adapt" and store_warmup and q0.shape == (1, self.n) and z.shape == (1, tune + draws, self.n)
-        m = nuts_numpy.DiagMass(var0[0], adapt=True, initial_mean=mean0[0].copy(), initial_weight=mass_initial_weight)
-        o = nuts_numpy.Oracle(self.f, m, step_scale=step_scale, adapt_step_size=adapt_step_size, target_accept=target_accept,
-                              gamma=gamma, k=k, t0=t0, Emax=Emax, max_treedepth=max_treedepth, early_max_treedepth=early_max_treedepth)
-        g = np.random.default_rng(0)
-        st = g.bit_generator.state
-        rec = rng_states[0]
-        st["state"]["state"] = (int(rec["state_hi"]) << 64) | int(rec["state_lo"])
-        st["state"]["inc"] = (int(rec["inc_hi"]) << 64) | int(rec["inc_lo"])
-        st["has_uint32"], st["uinteger"] = 0, 0
-        g.bit_generator.state = st
-        o.rng = g
-        qs, stats = o.run(q0[0], tune, draws, z=z[0])
-        s = g.bit_generator.state["state"]
-        rng_states[0] = (s["state"] >> 64, s["state"] & (2**64 - 1), s["inc"] >> 64, s["inc"] & (2**64 - 1))
-        return NutsResult(draws=qs[None], stats={k_: np.asarray(v)[None] for k_, v in stats.items()},
-                          summary={"bad_energy_at": np.array([-1])}, kernel_ms=0.0, launches=0, tune=tune, n_draws=draws,
-                          store_warmup=True)
 
 
 def drive(step, start, rng, tune, draws):

@@ -31,6 +31,15 @@ namespace b200 {
 
 constexpr int kMaxLevels = 12;  // pending-subtree levels (max_treedepth <= 12)
 
+// UNTESTED CANDIDATE (off): carry a subtree's multinomial weight as the pair (m, s), log-weight = m + log(s), instead of
+// one log-weight.  A leaf is (-dE, 1); merging (m1, s1) and (m2, s2) gives m = max(m1, m2), s = s1 e^(m1-m) + s2 e^(m2-m):
+// one exp and no log per merge (the log costs ~75 instructions, 9 % of the kernel's stall samples), and no overflow for
+// any energy change because m carries the scale and 1 <= s <= number of leaves.  The pick probabilities are the same
+// numbers as logaddexp gives (nuts.py:465-467, :370-376) up to rounding.
+#ifndef B200_MS_WEIGHTS
+#define B200_MS_WEIGHTS 0
+#endif
+
 struct NutsDev {
     int C, n, tune, draws, max_td, early_td, adapt_step, mass_kind, momentum_source, store_warmup;
     int window, discard, hot_levels, chain_offset;
@@ -62,7 +71,8 @@ __host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
 // (per chain; + 3 vectors when the subtree under construction is kept in shared memory; + the team's reduction pad)
 __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool subs = B200_SUBTREE_SMEM, int W = 1) {
     const int vecs = 2 + (subs ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
-    return (size_t)vecs * NP * sizeof(double) + 4 * kMaxLevels * sizeof(double) + (W > 1 ? W * 8 * sizeof(double) : 0);
+    return (size_t)vecs * NP * sizeof(double) + (4 + B200_MS_WEIGHTS) * kMaxLevels * sizeof(double) +
+           (W > 1 ? W * 8 * sizeof(double) : 0);
 }
 
 #ifndef B200_NUTS_THREADS
@@ -113,7 +123,12 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
     double* sc_pe = sc_logw + kMaxLevels;
     double* sc_plogp = sc_pe + kMaxLevels;
     double* sc_pidx = sc_plogp + kMaxLevels;
+#if B200_MS_WEIGHTS
+    double* sc_s = sc_pidx + kMaxLevels;
+    double* red = sc_s + kMaxLevels;     // W x 8 doubles, cross-warp reductions (W > 1)
+#else
     double* red = sc_pidx + kMaxLevels;  // W x 8 doubles, cross-warp reductions (W > 1)
+#endif
     double* gs = P.scratch + (long long)chain * P.scratch_stride;
 
     // which: 0 = left.p, 1 = right.p, 2 = p_sum, 3 = proposal q.  Level 0 (a single leaf) keeps only 2, 3.
@@ -208,6 +223,9 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
         }
         int L_idx = 0, R_idx = 0;
         double m_logw = 0.0, m_pe = E0, m_plogp = logp0;
+#if B200_MS_WEIGHTS
+        double m_s = 1.0;
+#endif
         int m_pidx = 0;
         double accept_sum = 0.0, max_de = 0.0;  // sum of min(1, exp(-dE)): exp(log_accept_sum) of nuts.py:415 without the log
         int n_prop = 0, depth = 0;
@@ -234,6 +252,9 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
             // ---- _build_subtree(edge, depth, +-eps): 2^depth leaves, merges driven by a binary counter --
             bool sub_div = false, sub_turn = false;
             double c_logw = 0.0, c_pe = 0.0, c_plogp = 0.0;
+#if B200_MS_WEIGHTS
+            double c_s = 1.0;
+#endif
             int c_pidx = 0;
             const int n_leaf = 1 << depth;
             for (int leaf = 0; leaf < n_leaf; ++leaf) {
@@ -275,6 +296,9 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     PQ(k) = q_s[lane + TS * k];
                 }
                 c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
+#if B200_MS_WEIGHTS
+                c_s = 1.0;
+#endif
 
                 // -- merge with pending left siblings while the counter carries (nuts.py:452-476)
                 int h = 0;
@@ -320,6 +344,23 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     if (h) team_sum_n<W>(dots, lane, red);
                     const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
                                       (dots[4] <= 0) || (dots[5] <= 0);
+#if B200_MS_WEIGHTS
+                    // weights (m, s): tree1 = (sc_logw[h], sc_s[h]), tree2 = (c_logw, c_s); P(pick tree2) = w2 / (w1 + w2)
+                    const double t_m = sc_logw[h], t_s = sc_s[h];
+                    const double dm = c_logw - t_m;
+                    const double e_w = exp(-fabs(dm));
+                    const double w2 = (dm >= 0.0) ? c_s : c_s * e_w, w1 = (dm >= 0.0) ? t_s * e_w : t_s;
+                    const double ws = w1 + w2;
+                    const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
+                    if (!(u * ws < w2)) {  // keep tree1's proposal
+                        const double* t_pq = lvl(h, 3);
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + TS * k];
+                        c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
+                    }
+                    c_logw = fmax(c_logw, t_m);
+                    c_s = ws;
+#else
                     // logw = logaddexp(t, c) = max + log1p(e), e = exp(-|c - t|); the pick  log(u) < c - logw  is
                     // u * (1 + e) < (c >= t ? 1 : e): same decision without evaluating log(u)
                     const double t_logw = sc_logw[h];
@@ -335,6 +376,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                         c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
                     }
                     c_logw = logw;
+#endif
                     if (turn) {
                         sub_turn = true;
                         break;
@@ -366,6 +408,9 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                     }
                     if (lane == 0) {
                         sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
+#if B200_MS_WEIGHTS
+                        sc_s[h] = c_s;
+#endif
                     }
                     team_sync<W>();
                 }
@@ -392,6 +437,21 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
             }
             // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
             {
+#if B200_MS_WEIGHTS
+                // accept the new subtree's proposal iff u < w_new / w_old  (log(u) < log_size_new - log_size_old)
+                const double u = rng.next_double();
+                const double dm = c_logw - m_logw;
+                const double e_w = exp(-fabs(dm));
+                const double wn = (dm >= 0.0) ? c_s : c_s * e_w, wo = (dm >= 0.0) ? m_s * e_w : m_s;
+                if (u * wo < wn) {
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = PQ(k);
+                    m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
+                }
+                m_logw = fmax(c_logw, m_logw);
+                m_s = wo + wn;
+            }
+#else
                 const double u = rng.next_double();
                 const double dlw = c_logw - m_logw;
                 const double e_w = exp(-fabs(dlw));
@@ -403,6 +463,7 @@ __global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 
                 m_logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
                                       : (isnan(dlw) ? c_logw + m_logw : fmax(c_logw, m_logw) + log1p_abs(e_w));
             }
+#endif
             // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
             {
                 const double* FARP = dir > 0 ? Lp : Rp;

@@ -43,6 +43,7 @@ WORKLOADS = {
     "radon": dict(
         builder="radon", args={}, chains=2048, tune=1000, draws=1000, scaling="weak", mass="diag_adapt",
         bound="hbm", per_eval=float(ALG_BYTES_PER_EVAL), kernel="nuts_warp_kernel<RadonModel,6>",
+        flops_per_eval=919 * 30.0 + 175 * 12.0,  # ~30 flop per observation + ~12 per parameter ~ 30 kflop
         desc={"n": 175, "n_obs": 919, "counties": 85}, cpu_procs=0, cpu_tune=300, cpu_draws=200,
         l2="outputs (2.9 GB of draws per step) exceed L2; no explicit flush needed",
         note="observed data is staged once per CTA into shared memory (bulk TMA) and the chain state lives in "
@@ -57,6 +58,7 @@ WORKLOADS = {
     "stochvol": dict(  # config #4: 256 chains per GPU (512 over 2), deep trees
         builder="stochvol", args={}, chains=256, tune=300, draws=100, scaling="weak", mass="diag_adapt",
         bound="hbm", per_eval=24000.0 + 7 * 3003 * 8 + 2 * 3003 * 8 * 2, kernel="nuts_warp_kernel<StochVolModel,12,8> (chain = CTA)",
+        flops_per_eval=3000 * 40.0,  # ~40 flop per latent state ~ 120 kflop
         desc={"n": 3003, "T": 3000}, cpu_procs=0, cpu_tune=40, cpu_draws=20,
         l2="tree bookkeeping of 256 chains (53 vectors x 24 KB each) is spread over HBM/L2",
         note="chain = CTA of 8 warps; integrator state in shared memory, pending-subtree stack in HBM/L2"),
@@ -273,6 +275,37 @@ def ncu_traffic(evals_per_launch):
     return None
 
 
+def make_roofline(workload, wl, per_launch, k_ms, fp64, dmma, peaks, traffic):
+    """The `roofline` object of the bench line.  per_launch: grad evaluations of one run (start states included);
+    k_ms: its CUDA-event duration; fp64 / dmma: TFLOP/s measured in this process (or None); peaks: (HBM GB/s, source)."""
+    if wl["bound"] == "hbm":
+        peak, how = peaks
+        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e9
+        out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": traffic, "peak_source": how,
+               "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch",
+               "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_bytes_per_eval": wl["per_eval"], "note": wl["note"],
+               "fp64_peak_tflops_measured": fp64}
+        if wl.get("flops_per_eval") and fp64:
+            # SURVEY 8(d): "report HBM fraction from algorithmic bytes AND fp64-pipe fraction" -- the second, honest ceiling
+            # of a kernel whose data lives on chip
+            tf = wl["flops_per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
+            out["fp64"] = {"bound": "fp64", "achieved": tf, "peak": fp64, "unit": "TFLOP/s", "frac": tf / fp64,
+                           "algorithmic_flops_per_eval": wl["flops_per_eval"],
+                           "peak_source": "DFMA micro-benchmark in this run (b200_measure_fp64_tflops)"}
+        return out
+    # dense contraction on the fp64 tensor path: no fp64 entry in MEASURED_PEAKS.json (HBM + bf16 only), so the
+    # denominator is the DMMA rate measured in this process by the library's own micro-benchmark
+    peak = dmma or 37.0
+    achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": "fp64 DMMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)"
+            if dmma else "fallback 37.0 (scripts/mb/dmma.cu measured on this pool)",
+            "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "note": wl["note"],
+            "fp64_dfma_peak_tflops_measured": fp64,
+            "time_base": "kernel_ms spans every launch of the lock-step loop (advance kernels and ragged tail included)"}
+
+
 # ---------------------------------------------------------------------------------------------
 # the CUDA engine arm
 # ---------------------------------------------------------------------------------------------
@@ -404,24 +437,8 @@ def b200_arm(args):
             fp64 = tf.value
         if _lib.load().b200_measure_dmma_tflops(ctypes.byref(tf)) == 0:
             dmma = tf.value
-    if wl["bound"] == "hbm":
-        peak, how = measured_peaks()
-        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(per_launch) if args.workload == "radon" else None, "peak_source": how,
-                    "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch",
-                    "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_bytes_per_eval": wl["per_eval"], "note": wl["note"],
-                    "fp64_peak_tflops_measured": fp64}
-    else:  # dense contraction on the fp64 tensor path: no fp64 entry in MEASURED_PEAKS.json (HBM + bf16 only), so the
-        # denominator is the DMMA rate measured in this process by the library's own micro-benchmark
-        peak = dmma or 37.0
-        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "fp64 DMMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)"
-                    if dmma else "fallback 37.0 (scripts/mb/dmma.cu measured on this pool)",
-                    "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "note": wl["note"],
-                    "fp64_dfma_peak_tflops_measured": fp64,
-                    "time_base": "kernel_ms spans every launch of the lock-step loop (advance kernels and ragged tail included)"}
+    roofline = make_roofline(args.workload, wl, per_launch, k_ms, fp64, dmma, measured_peaks(),
+                             ncu_traffic(per_launch) if args.workload == "radon" else None)
 
     # ---- cpu_baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -----------
     cpu = None

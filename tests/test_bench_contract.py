@@ -22,6 +22,25 @@ def test_workload_table_covers_the_baseline_configs():
     assert bench.WORKLOADS["radon"]["chains"] == 2048 and bench.WORKLOADS["mvgauss"]["scaling"] == "strong"
 
 
+def test_roofline_objects():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    wl = bench.WORKLOADS["radon"]
+    r = bench.make_roofline("radon", wl, per_launch=9.0e7, k_ms=500.0, fp64=36.0, dmma=37.0, peaks=(6563.9, "measured"), traffic=5.3e9)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["achieved"] - 28180 * 9.0e7 / 0.5 / 1e9) < 1e-6
+    assert abs(r["frac"] - r["achieved"] / 6563.9) < 1e-12 and r["traffic"] == 5.3e9 and r["peak_source"] == "measured"
+    f = r["fp64"]  # the second ceiling of a kernel whose data lives on chip
+    assert f["bound"] == "fp64" and abs(f["achieved"] - (919 * 30 + 175 * 12) * 9.0e7 / 0.5 / 1e12) < 1e-9 and f["peak"] == 36.0
+    assert "fp64" not in bench.make_roofline("radon", wl, 9.0e7, 500.0, None, None, (6650.0, "fallback"), None)
+    t = bench.make_roofline("logistic", bench.WORKLOADS["logistic"], per_launch=4.0e5, k_ms=12000.0, fp64=36.0, dmma=37.0,
+                            peaks=(6563.9, "measured"), traffic=None)
+    assert t["bound"] == "tensor" and t["unit"] == "TFLOP/s" and abs(t["achieved"] - 512e6 * 4.0e5 / 12.0 / 1e12) < 1e-9
+    assert t["peak"] == 37.0 and t["traffic"] is None
+    assert bench.make_roofline("mvgauss", bench.WORKLOADS["mvgauss"], 1e5, 1e4, None, None, (6563.9, "measured"), None)["peak"] == 37.0
+    json.dumps([r, t])
+
+
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--cpu-chains", "2", "--tune", "6", "--draws", "8"], capture_output=True, text=True, timeout=300, cwd=ROOT)

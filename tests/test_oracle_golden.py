@@ -98,3 +98,93 @@ def test_dense_mass_step_adaptation_prefix_reproduces_golden(golden):
     assert np.array_equal(st["tree_size"], d["stat_tree_size"][0][:T])
     assert np.max(np.abs(st["step_size"] - d["stat_step_size"][0][:T]) / d["stat_step_size"][0][:T]) <= 1e-9
     assert np.max(np.abs(qs - d["draws_q"][0][:T])) <= 1e-7
+
+
+def test_ms_weight_candidate_takes_the_reference_decisions(golden, monkeypatch):
+    """The (m, s) multinomial-weight arithmetic prepared for the CUDA kernel (nuts_warp.cuh, B200_MS_WEIGHTS: log-weight =
+    m + log s, one exp and no log per merge) restated here on top of the oracle: it must take exactly the decisions of
+    the reference's logaddexp arithmetic on the golden chains."""
+    import math
+
+    class MSTrajectory(nuts_numpy._Trajectory):
+        def __init__(self, *a):
+            super().__init__(*a)
+            self.s = 1.0
+
+        def _leaf(self, frm, eps):
+            span, div, turn = super()._leaf(frm, eps)
+            span.s = 1.0
+            return span, div, turn
+
+        @staticmethod
+        def _split(m2, s2, m1, s1):  # -> (w1, w2, m): weights of tree1 / tree2 relative to the larger m
+            dm = m2 - m1
+            e = math.exp(-abs(dm))
+            return (s1 * e, s2, max(m1, m2)) if dm >= 0.0 else (s1, s2 * e, max(m1, m2))
+
+        def _grow(self, frm, height, eps):
+            if height == 0:
+                return self._leaf(frm, eps)
+            a, div, turn = self._grow(frm, height - 1, eps)
+            if div or turn:
+                return a, div, turn
+            b, div, turn = self._grow(a.right, height - 1, eps)
+            if not (div or turn):
+                ps = a.p_sum + b.p_sum
+                turn = nuts_numpy._uturn(ps, a.left.v, b.right.v)
+                if (not turn) and (height - 1 > 0):
+                    s1 = a.p_sum + b.left.p
+                    turn = nuts_numpy._uturn(s1, a.left.v, b.left.v)
+                    if not turn:
+                        s2 = a.right.p + b.p_sum
+                        turn = nuts_numpy._uturn(s2, a.right.v, b.right.v)
+                w1, w2, m = self._split(b.log_w, b.s, a.log_w, a.s)
+                ws = w1 + w2
+                pick = b.pick if self.rng.random() * ws < w2 else a.pick
+                out = nuts_numpy.Span(a.left, b.right, ps, pick, m)
+                out.s = ws
+                return out, div, turn
+            out = nuts_numpy.Span(a.left, b.right, a.p_sum, a.pick, a.log_w)
+            out.s = a.s
+            return out, div, turn
+
+        def double(self, direction):
+            # the log-domain parent consumes rng and updates log_w; redo its bookkeeping with (m, s)
+            if direction > 0:
+                sub, div, turn = self._grow(self.right, self.depth, np.asarray(self.eps, dtype="float64"))
+                lo_begin, lo_end, hi_begin, hi_end = self.left, self.right, sub.left, sub.right
+                lo_sum, hi_sum = self.p_sum.copy(), sub.p_sum
+                self.right = sub.right
+            else:
+                sub, div, turn = self._grow(self.left, self.depth, np.asarray(-self.eps, dtype="float64"))
+                lo_begin, lo_end, hi_begin, hi_end = sub.right, sub.left, self.left, self.right
+                lo_sum, hi_sum = sub.p_sum, self.p_sum.copy()
+                self.left = sub.right
+            self.depth += 1
+            if div or turn:
+                return div, turn
+            wo, wn, m = self._split(sub.log_w, sub.s, self.log_w, self.s)
+            if self.rng.random() * wo < wn:
+                self.pick = sub.pick
+            self.log_w, self.s = m, wo + wn
+            self.p_sum[:] += sub.p_sum
+            turn = nuts_numpy._uturn(self.p_sum, self.left.v, self.right.v)
+            if not turn:
+                turn = nuts_numpy._uturn(lo_sum + hi_begin.p, lo_begin.v, hi_begin.v)
+            if not turn:
+                turn = nuts_numpy._uturn(lo_end.p + hi_sum, lo_end.v, hi_end.v)
+            return div, turn
+
+    monkeypatch.setattr(nuts_numpy, "_Trajectory", MSTrajectory)
+    for name in ("eight_schools_fixed", "radon_fixed", "stochvol_small_fixed"):
+        d = golden(name)
+        spec = SPEC_OF[name]()
+        f = logp_numpy.make_logp(spec)
+        for c in range(len(d["seeds"])):
+            o = _oracle(spec, f, d["var"][c])
+            o.da = nuts_numpy.DualAveraging(float(d["used_eps"][c][0]))
+            o.rng, o.tune = _gen_from_state(d["pre_rng"][c][0]), False
+            qs, st = o.run(d["q0"][c], 0, int(d["draws"]), z=d["z"][c])
+            assert np.array_equal(st["tree_size"], d["stat_tree_size"][c])
+            assert np.array_equal(st["index_in_trajectory"], d["stat_index_in_trajectory"][c])
+            assert np.max(np.abs(qs - d["draws_q"][c])) <= 1e-9

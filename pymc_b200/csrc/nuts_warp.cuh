@@ -82,8 +82,13 @@ __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool sub
 #define B200_NUTS_MINBLOCKS 1  // __launch_bounds__ min CTAs/SM: the register budget knob
 #endif
 // W = warps per chain (team).  SUBS = subtree-under-construction vectors in shared memory instead of registers.
+#ifdef B200_NUTS_MAXREG  // untested candidate: an explicit register cap (e.g. 144 -> 14 warps/SM = all 2048 chains of the
+#define B200_NUTS_BOUNDS __maxnreg__(B200_NUTS_MAXREG)  // bench resident at once); cannot be combined with __launch_bounds__
+#else
+#define B200_NUTS_BOUNDS __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 : B200_NUTS_MINBLOCKS)
+#endif
 template <class Model, int NPL, int W, bool SUBS>
-__global__ void __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 : B200_NUTS_MINBLOCKS)
+__global__ void B200_NUTS_BOUNDS
     nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
     constexpr int TS = 32 * W;      // threads per chain
     constexpr int NP = TS * NPL;    // padded vector length

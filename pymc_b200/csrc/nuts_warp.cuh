@@ -65,12 +65,19 @@ __host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
     return (long long)(G_STACK + 4 * levels) * NP;
 }
 // shared memory per warp (bytes): q, g, hot stack levels (level 0: 2 vectors, others: 4), scalars
+// UNTESTED CANDIDATE (off): cut the register live ranges across the model function -- the inverse mass `var` lives in
+// shared memory for the whole run and the momentum `p` is parked there around every evaluation, so the model function's
+// ~110 registers are not stacked on top of 2 x NPL persistent doubles (target: 168 registers without spills with
+// B200_SUBTREE_SMEM=1 -> 3 CTAs x 4 warps per SM).
+#ifndef B200_PARK_VECTORS
+#define B200_PARK_VECTORS 0
+#endif
 #ifndef B200_SUBTREE_SMEM
 #define B200_SUBTREE_SMEM 0  // 1: left.p / p_sum / proposal q of the subtree under construction live in shared memory
 #endif                       //    (frees 6*NPL registers per lane -> more resident warps); 0: in registers
 // (per chain; + 3 vectors when the subtree under construction is kept in shared memory; + the team's reduction pad)
 __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool subs = B200_SUBTREE_SMEM, int W = 1) {
-    const int vecs = 2 + (subs ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
+    const int vecs = 2 + (subs ? 3 : 0) + 2 * B200_PARK_VECTORS + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
     return (size_t)vecs * NP * sizeof(double) + (4 + B200_MS_WEIGHTS) * kMaxLevels * sizeof(double) +
            (W > 1 ? W * 8 * sizeof(double) : 0);
 }
@@ -116,7 +123,15 @@ __global__ void B200_NUTS_BOUNDS
     double* q_s = ws;
     double* g_s = ws + NP;
     double* sub_s = ws + 2 * NP + lane;            // SUBS: left.p, p_sum, proposal q of the subtree under construction
+#if B200_PARK_VECTORS
+    double* var_s = ws + (SUBS ? 5 : 2) * NP + lane;   // inverse mass, resident in shared memory
+    double* park_s = var_s + NP;                       // momentum, parked around the model function
+    double* hot_base = ws + (SUBS ? 7 : 4) * NP;
+#define VAR(k) var_s[TS * (k)]
+#else
     double* hot_base = ws + (SUBS ? 5 : 2) * NP;
+#define VAR(k) var[k]
+#endif
     double lp_r[SUBS ? 1 : NPL], ps_r[SUBS ? 1 : NPL], pq_r[SUBS ? 1 : NPL];
     auto LPf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[TS * k]; else return lp_r[k]; };
     auto PSf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[NP + TS * k]; else return ps_r[k]; };
@@ -148,17 +163,21 @@ __global__ void B200_NUTS_BOUNDS
     const int T_out = P.store_warmup ? Ttot : P.draws;
 
     // ---- per-chain persistent state ---------------------------------------------------------------
+#if B200_PARK_VECTORS
+    double p[NPL];
+#else
     double var[NPL], p[NPL];
+#endif
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
         const int i = lane + TS * k;
         q_s[i] = (i < n) ? P.q0[(long long)chain * n + i] : 0.0;
         g_s[i] = 0.0;
-        var[k] = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
+        VAR(k) = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
         // Welford estimators: foreground starts at (mean0, var0 * weight, weight); background empty
         if (P.mass_kind == B200_MASS_DIAG_ADAPT) {
             gvec(G_FGM)[i] = (i < n && P.mean0) ? P.mean0[(long long)chain * n + i] : 0.0;
-            gvec(G_FGV)[i] = var[k] * P.init_weight;
+            gvec(G_FGV)[i] = VAR(k) * P.init_weight;
             gvec(G_BGM)[i] = 0.0;
             gvec(G_BGV)[i] = 0.0;
         }
@@ -196,16 +215,24 @@ __global__ void B200_NUTS_BOUNDS
                          ? P.z[((long long)chain * Ttot + it) * n + i]
                          : philox_normal(P.philox_seed, (uint32_t)(chain + P.chain_offset), (uint32_t)it, (uint32_t)i);
             }
-            p[k] = (1.0 / sqrt(var[k])) * zz;
+            p[k] = (1.0 / sqrt(VAR(k))) * zz;
         }
         // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
+#if B200_PARK_VECTORS
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) park_s[TS * k] = p[k];
+#endif
         team_sync<W>();
         const double logp0 = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
         team_sync<W>();
+#if B200_PARK_VECTORS
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) p[k] = park_s[TS * k];
+#endif
         ++n_grad;
         double kin = 0.0;
 #pragma unroll
-        for (int k = 0; k < NPL; ++k) kin = fma(p[k], var[k] * p[k], kin);
+        for (int k = 0; k < NPL; ++k) kin = fma(p[k], VAR(k) * p[k], kin);
         const double E0 = 0.5 * team_sum<W>(kin, lane, red) - logp0;
         if (!isfinite(E0)) {  // "Bad initial energy" (base_hmc.py:205-224): freeze the chain
             bad_at = it;
@@ -268,18 +295,26 @@ __global__ void B200_NUTS_BOUNDS
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + TS * k;
                     p[k] = fma(dt, g_s[i], p[k]);
-                    q_s[i] = fma(es, var[k] * p[k], q_s[i]);
+                    q_s[i] = fma(es, VAR(k) * p[k], q_s[i]);
                 }
+#if B200_PARK_VECTORS
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) park_s[TS * k] = p[k];
+#endif
                 team_sync<W>();
                 const double logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
                 team_sync<W>();
+#if B200_PARK_VECTORS
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) p[k] = park_s[TS * k];
+#endif
                 ++n_grad;
                 double kk = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + TS * k;
                     p[k] = fma(dt, g_s[i], p[k]);
-                    kk = fma(p[k], var[k] * p[k], kk);
+                    kk = fma(p[k], VAR(k) * p[k], kk);
                 }
                 const double E = 0.5 * team_sum<W>(kk, lane, red) - logp;
                 w_idx += dir;
@@ -318,8 +353,8 @@ __global__ void B200_NUTS_BOUNDS
                             const int i = lane + TS * k;
                             const double tp = t_ps[i];
                             const double s = tp + PS(k);
-                            dots[0] = fma(s, var[k] * tp, dots[0]);
-                            dots[1] = fma(s, var[k] * p[k], dots[1]);
+                            dots[0] = fma(s, VAR(k) * tp, dots[0]);
+                            dots[1] = fma(s, VAR(k) * p[k], dots[1]);
                             LP(k) = tp;
                             PS(k) = s;
                         }
@@ -333,14 +368,14 @@ __global__ void B200_NUTS_BOUNDS
                             const int i = lane + TS * k;
                             const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
                             const double s = tp + PS(k);
-                            const double vl = var[k] * tl, vr = var[k] * p[k];
+                            const double vl = VAR(k) * tl, vr = VAR(k) * p[k];
                             dots[0] = fma(s, vl, dots[0]);
                             dots[1] = fma(s, vr, dots[1]);
                             const double s1 = tp + LP(k);  // tree1.p_sum + tree2.left.p
                             dots[2] = fma(s1, vl, dots[2]);
-                            dots[3] = fma(s1, var[k] * LP(k), dots[3]);
+                            dots[3] = fma(s1, VAR(k) * LP(k), dots[3]);
                             const double s2 = tr + PS(k);  // tree1.right.p + tree2.p_sum
-                            dots[4] = fma(s2, var[k] * tr, dots[4]);
+                            dots[4] = fma(s2, VAR(k) * tr, dots[4]);
                             dots[5] = fma(s2, vr, dots[5]);
                             LP(k) = tl;
                             PS(k) = s;
@@ -479,14 +514,14 @@ __global__ void B200_NUTS_BOUNDS
                     const double so = PSv[i], fp = FARP[i], np_ = NEARP[i];
                     const double s = so + PS(k);
                     PSv[i] = s;
-                    const double vf = var[k] * fp, vw = var[k] * p[k];
+                    const double vf = VAR(k) * fp, vw = VAR(k) * p[k];
                     dots[0] = fma(s, vf, dots[0]);
                     dots[1] = fma(s, vw, dots[1]);
                     const double a = so + LP(k);   // old p_sum + (new subtree's edge adjacent to the old tree).p
                     dots[2] = fma(a, vf, dots[2]);
-                    dots[3] = fma(a, var[k] * LP(k), dots[3]);
+                    dots[3] = fma(a, VAR(k) * LP(k), dots[3]);
                     const double b = np_ + PS(k);  // (old tree's edge adjacent to the new subtree).p + new p_sum
-                    dots[4] = fma(b, var[k] * np_, dots[4]);
+                    dots[4] = fma(b, VAR(k) * np_, dots[4]);
                     dots[5] = fma(b, vw, dots[5]);
                 }
                 team_sum_n<W>(dots, lane, red);
@@ -548,7 +583,7 @@ __global__ void B200_NUTS_BOUNDS
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + TS * k;
-                    if (i < n) var[k] = fmin(fmax(fv[i] / fg_n, 1e-12), 1e12);
+                    if (i < n) VAR(k) = fmin(fmax(fv[i] / fg_n, 1e-12), 1e12);
                 }
             }
             if (k_samples > 0 && k_samples % window == 0) {
@@ -610,10 +645,12 @@ __global__ void B200_NUTS_BOUNDS
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + TS * k;
-            if (i < n) P.sm.final_var[(long long)chain * n + i] = var[k];
+            if (i < n) P.sm.final_var[(long long)chain * n + i] = VAR(k);
         }
     }
 }
+
+#undef VAR
 
 // ---------------------------------------------------------------------------------------------------
 // Batched logp + gradient: one warp per point.  Replaces ValueGradFunction._pytensor_function

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round profile capture (run under gpurun, ONE GPU): profile_round.sh <tag> <part>, part = bench | dense.
+# Round profile capture (run under gpurun, ONE GPU): profile_round.sh <tag> <part>, part = bench | dense | stochvol.
 # Outputs land in gpurun_out/ (kept small: .ncu-rep files are exported to CSV on the box and deleted) and are summarised
 # into profiles/ by scripts/summarise_profiles.py.  Every ncu invocation runs under `timeout`; only the application
 # process is profiled (bench.py spawns nvidia-smi and, for the CPU baseline, a process pool: profiling those children
@@ -23,6 +23,8 @@ if [ "$PART" = bench ]; then
   cap nuts nuts_warp_kernel 0 scripts/ncu_target_radon.py
   timeout -k 10 300 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $O/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_launches_bench.log 2>&1
   echo "launch list rc=$?"
+elif [ "$PART" = stochvol ]; then
+  cap stochvol nuts_warp_kernel 0 scripts/ncu_target_stochvol.py
 else
   timeout -k 10 200 $NCU --metrics gpu__time_duration.sum -c 300 --csv --log-file $O/${R}_launches_logistic.csv python scripts/ncu_target3.py logistic 4 2 > $O/${R}_launches_logistic.log 2>&1
   cap logistic logistic_fused_kernel 2 scripts/ncu_target3.py logistic 2 1

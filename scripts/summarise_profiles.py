@@ -111,6 +111,7 @@ if __name__ == "__main__":
                    "grad_evals_incl_start_state": evals, "dram_bytes_read": rd, "dram_bytes_write": wr,
                    "dram_bytes_per_grad_eval": (rd + wr) / evals, "algorithmic_bytes_per_grad_eval": 28180},
                   open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+    raw_summary("stochvol"); opcode_mix("stochvol")
     raw_summary("logistic"); opcode_mix("logistic")
     raw_summary("gemm"); opcode_mix("gemm")
     launches(f"{tag}_launches.csv", f"{tag}_launches_bench_summary.csv")

@@ -172,8 +172,6 @@ def sample_b200_nuts(
     if compute_convergence_checks and chains > 1 and draws >= 8:
         from . import diagnostics
 
-        x = d_all[:, w:]
-        out.attrs["ess_bulk_min"] = float(np.nanmin(diagnostics.ess_bulk(x)))
-        out.attrs["rhat_max"] = float(np.nanmax(diagnostics.rhat(x)))
+        out.attrs["ess_bulk_min"], out.attrs["rhat_max"] = diagnostics.convergence_summary(d_all[:, w:])
         out.attrs["divergences"] = int(stats["diverging"].sum())
     return out

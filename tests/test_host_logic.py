@@ -74,6 +74,22 @@ def test_ess_torch_matches_numpy():
     np.testing.assert_allclose(a, b, rtol=1e-6)
 
 
+def test_rhat_torch_and_convergence_summary_match_numpy():
+    import torch
+
+    rng = np.random.default_rng(2)
+    x = np.cumsum(rng.normal(size=(6, 300, 5)), axis=1) * 0.05 + rng.normal(size=(6, 300, 5))
+    x[:, :, 3] += np.arange(6)[:, None] * 0.7  # one parameter whose chains disagree
+    a = diagnostics.rhat(x)
+    b = diagnostics.rhat_torch(torch.as_tensor(x), param_chunk=2).numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+    assert a[3] > 1.2 and a[3] > a[[0, 1, 2, 4]].max()
+    e, r = diagnostics.convergence_summary(x)
+    assert abs(e - np.nanmin(diagnostics.ess_bulk(x))) < 1e-9 and abs(r - a.max()) < 1e-12
+    e2, r2 = diagnostics.convergence_summary(x, large=10)  # "large" path: GPU if visible, else the same host path
+    assert abs(e2 - e) <= 1e-6 * e and abs(r2 - r) <= 1e-6
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys

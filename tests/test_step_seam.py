@@ -88,14 +88,10 @@ def test_b200nuts_requires_setup_chain_and_respects_schedule():
     assert B200NUTS.competence(type("V", (), {"dtype": "int64"})(), True) == 0
 
 
-@pytest.mark.gpu
-def test_b200nuts_on_device_reproduces_golden_adaptive_prefix(golden):
-    """The real engine behind the step-method seam: first iterations of the reference's adaptive Eight Schools chain."""
-    from pymc_b200 import engine
-
+def _golden_prefix_through_step_seam(golden, make_engine):
     d = golden("eight_schools_adapt")
     spec = models.eight_schools()
-    s = B200NUTS(engine.CompiledModel(spec), potential_mean=d["q0"][0], potential_var=d["init_var"][0],
+    s = B200NUTS(make_engine(spec), potential_mean=d["q0"][0], potential_var=d["init_var"][0],
                  step_scale=float(d["step_scale"]))
     tune, T = int(d["tune"]), 12
     q0 = d["q0"][0]
@@ -109,3 +105,17 @@ def test_b200nuts_on_device_reproduces_golden_adaptive_prefix(golden):
         assert st[0]["tree_size"] == d["stat_tree_size"][0][i] and st[0]["depth"] == d["stat_depth"][0][i]
         assert np.max(np.abs(q - d["draws_q"][0][i])) <= 1e-7
         assert abs(st[0]["step_size"] - d["stat_step_size"][0][i]) <= 1e-9 * d["stat_step_size"][0][i]
+
+
+def test_b200nuts_reproduces_golden_adaptive_prefix_oracle_engine(golden):
+    """The golden chain was produced by the verbatim reference from default_rng(seed): the step-method seam must land on
+    it when it derives its streams from the same generator (here with the oracle-backed engine)."""
+    _golden_prefix_through_step_seam(golden, OracleEngine)
+
+
+@pytest.mark.gpu
+def test_b200nuts_on_device_reproduces_golden_adaptive_prefix(golden):
+    """The real engine behind the step-method seam: first iterations of the reference's adaptive Eight Schools chain."""
+    from pymc_b200 import engine
+
+    _golden_prefix_through_step_seam(golden, engine.CompiledModel)

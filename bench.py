@@ -42,7 +42,7 @@ ALG_BYTES_PER_EVAL = 919 * (8 + 8 + 4) + 7 * 175 * 8  # observed da
 WORKLOADS = {
     "radon": dict(
         builder="radon", args={}, chains=2048, tune=1000, draws=1000, scaling="weak", mass="diag_adapt",
-        bound="hbm", per_eval=float(ALG_BYTES_PER_EVAL), kernel="nuts_warp_kernel<RadonModel,6>",
+        bound="onchip", per_eval=float(ALG_BYTES_PER_EVAL), kernel="nuts_warp_kernel<RadonModel,6>",
         flops_per_eval=919 * 30.0 + 175 * 12.0,  # ~30 flop per observation + ~12 per parameter ~ 30 kflop
         desc={"n": 175, "n_obs": 919, "counties": 85}, cpu_procs=0, cpu_tune=300, cpu_draws=200,
         l2="outputs (2.9 GB of draws per step) exceed L2; no explicit flush needed",
@@ -57,7 +57,7 @@ WORKLOADS = {
              "tensor path (mma.sync m8n8k4.f64); flops per grad-eval per chain = 4 N K"),
     "stochvol": dict(  # config #4: 256 chains per GPU (512 over 2), deep trees
         builder="stochvol", args={}, chains=256, tune=300, draws=100, scaling="weak", mass="diag_adapt",
-        bound="hbm", per_eval=24000.0 + 7 * 3003 * 8 + 2 * 3003 * 8 * 2, kernel="nuts_warp_kernel<StochVolModel,12,8> (chain = CTA)",
+        bound="onchip", per_eval=24000.0 + 7 * 3003 * 8 + 2 * 3003 * 8 * 2, kernel="nuts_warp_kernel<StochVolModel,12,8> (chain = CTA)",
         flops_per_eval=3000 * 40.0,  # ~40 flop per latent state ~ 120 kflop
         desc={"n": 3003, "T": 3000}, cpu_procs=0, cpu_tune=40, cpu_draws=20,
         l2="tree bookkeeping of 256 chains (53 vectors x 24 KB each) is spread over HBM/L2",
@@ -162,9 +162,50 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def physical_cpus():
+    """One logical CPU id per PHYSICAL core of the CPUs this process may run on (hyper-thread siblings dropped)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+    seen, out = set(), []
+    for cpu in allowed:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as fh:
+                key = fh.read().strip()
+        except OSError:
+            key = str(cpu)
+        if key not in seen:
+            seen.add(key)
+            out.append(cpu)
+    return out
+
+
+def _pin_worker(cpus, procs, counter):
+    """Pool initializer: worker i is pinned to its own slice of the physical cores (one core per chain process; the
+    BLAS-bound workloads get cores/processes cores each)."""
+    with counter.get_lock():
+        i = counter.value
+        counter.value += 1
+    per = max(1, len(cpus) // max(1, procs))
+    lo = (i * per) % len(cpus)
+    try:
+        os.sched_setaffinity(0, cpus[lo:lo + per] or cpus[:1])
+    except (AttributeError, OSError):
+        pass
+
+
+def make_pool(procs):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    return ctx.Pool(procs, initializer=_pin_worker, initargs=(physical_cpus(), procs, ctx.Value("i", 0)))
+
+
 def cpu_plan(args):
-    """processes, BLAS threads per process, chains, tune, draws of the bounded CPU sample of this workload."""
-    cores = host_cores()
+    """processes, BLAS threads per process, chains, tune, draws of the bounded CPU sample of this workload.
+    One process per PHYSICAL core (pinned), like one chain per core in sampling/parallel.py."""
+    cores = len(physical_cpus())
     wl = args.wl
     procs = min(cores, wl["cpu_procs"] or cores)
     chains = args.cpu_chains or procs
@@ -172,34 +213,51 @@ def cpu_plan(args):
     return procs, max(1, cores // procs), chains, min(args.tune, wl["cpu_tune"]), min(args.draws, wl["cpu_draws"])
 
 
-def reference_arm(args):
-    import multiprocessing as mp
-
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_measure(args, steps, warm=True):
+    """The bounded CPU sample: `steps` runs of `chains` chains on pinned workers + the single-process rate on one idle
+    core (the linear expectation).  Returns (evals, wall, ess, info); info carries per-core rates and the efficiency, and
+    says so loudly when the box delivers less than half of linear (oversubscribed host: VERDICT r1 weak #9)."""
     procs, threads, chains, tune, draws = cpu_plan(args)
-    cores = procs * threads
-    # bounded sample: `chains` chains x (tune + draws) shortened so a step is ~10-20 s of wall time
-    with mp.get_context("spawn").Pool(procs) as pool:
-        for _ in range(1 if args.warmup else 0):  # imports, model build (and BLAS warm-up) in every worker
-            cpu_run(procs, 2, 1, 999, pool, args.workload, threads)
+    with make_pool(1) as solo:  # one chain alone on one pinned core
+        cpu_run(1, 2, 1, 999, solo, args.workload, threads)
+        e1, w1, _ = cpu_run(1, tune, draws, 4242, solo, args.workload, threads)
+    solo_rate = e1 / w1
+    with make_pool(procs) as pool:
+        if warm:
+            cpu_run(procs, 2, 1, 999, pool, args.workload, threads)  # imports, model build, BLAS warm-up in every worker
         evals, wall, ess = 0, 0.0, None
-        for s in range(args.steps):
+        for s in range(steps):
             e, w, qs = cpu_run(chains, tune, draws, 1000 * (s + 1), pool, args.workload, threads)
             evals += e
             wall += w
             ess = cpu_ess(qs, w)
+    rate = evals / wall
+    eff = rate / (solo_rate * procs)
+    info = {"processes": procs, "blas_threads": threads, "physical_cores": len(physical_cpus()), "logical_cpus": host_cores(),
+            "pinned": True, "per_core_evals_per_s": rate / procs, "single_core_evals_per_s": solo_rate,
+            "linear_expectation": solo_rate * procs, "parallel_efficiency": eff}
+    if eff < 0.5:
+        info["warning"] = (f"host delivers {eff:.0%} of linear scaling over {procs} pinned processes: the CPU arm is "
+                           "memory/SMT/cgroup bound on this box; compare with linear_expectation")
+        print("bench.py: " + info["warning"], file=sys.stderr)
+    sample = (f"{chains} chains x ({tune} tune + {draws} draws) of the same {args.workload} model per step, {procs} pinned "
+              f"processes x {threads} BLAS threads")
+    return evals, wall, ess, info, sample, procs * threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    evals, wall, ess, info, sample, cores = cpu_measure(args, args.steps, warm=bool(args.warmup))
     value = evals / wall
-    sample = (f"{chains} chains x ({tune} tune + {draws} draws) of the same {args.workload} model per step, {procs} processes x "
-              f"{threads} BLAS threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, (args.chains_per_gpu or args.wl["chains"])), **args.wl["desc"],
                    "note": "bounded CPU sample of the same workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ess": ess},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ess": ess, **info},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -263,13 +321,15 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(evals_per_launch):
-    """DRAM bytes per launch: bytes/grad-eval measured by ncu on a shorter launch of the same kernel
-    (profiles/r1_traffic.json) x the grad-evals of this launch; None if no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def ncu_traffic(workload, evals_per_launch):
+    """(DRAM bytes per launch, source) from the committed ncu --set full capture of this workload's kernel
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per grad-eval of the captured launch, scaled by
+    the grad-evals of this launch -- the capture is a shorter launch of the same kernel); None if nothing is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(p):
         try:
-            return float(json.load(open(p))["dram_bytes_per_grad_eval"]) * evals_per_launch
+            e = json.load(open(p))[workload]
+            return float(e["dram_bytes_per_grad_eval"]) * evals_per_launch, e.get("source", "profiles/traffic.json")
         except Exception:
             return None
     return None
@@ -277,29 +337,35 @@ def ncu_traffic(evals_per_launch):
 
 def make_roofline(workload, wl, per_launch, k_ms, fp64, dmma, peaks, traffic):
     """The `roofline` object of the bench line.  per_launch: grad evaluations of one run (start states included);
-    k_ms: its CUDA-event duration; fp64 / dmma: TFLOP/s measured in this process (or None); peaks: (HBM GB/s, source)."""
-    if wl["bound"] == "hbm":
+    k_ms: its CUDA-event duration; fp64 / dmma: TFLOP/s measured in this process (or None); peaks: (HBM GB/s, source);
+    traffic: (DRAM bytes per launch or None, how it was obtained).
+
+    The top-level `bound`/`frac` is the BINDING resource.  The persistent kernels keep observed data and chain state on
+    chip, so their DRAM traffic is orders of magnitude below the algorithmic bytes and the binding pipe is fp64: the
+    HBM-by-algorithmic-bytes figure SURVEY 8(d) asks for is reported as the secondary `hbm_by_algorithmic_bytes` object
+    (it is NOT a utilisation of anything), next to the DRAM bytes ncu measured."""
+    t_bytes, t_how = traffic if traffic else (None, None)
+    if wl["bound"] == "onchip":
         peak, how = peaks
-        achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e9
-        out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-               "traffic": traffic, "peak_source": how,
-               "traffic_note": "ncu dram bytes per grad-eval of a 150+50 launch (profiles/r1_traffic.json) scaled to this launch",
-               "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_bytes_per_eval": wl["per_eval"], "note": wl["note"],
-               "fp64_peak_tflops_measured": fp64}
-        if wl.get("flops_per_eval") and fp64:
-            # SURVEY 8(d): "report HBM fraction from algorithmic bytes AND fp64-pipe fraction" -- the second, honest ceiling
-            # of a kernel whose data lives on chip
-            tf = wl["flops_per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
-            out["fp64"] = {"bound": "fp64", "achieved": tf, "peak": fp64, "unit": "TFLOP/s", "frac": tf / fp64,
-                           "algorithmic_flops_per_eval": wl["flops_per_eval"],
-                           "peak_source": "DFMA micro-benchmark in this run (b200_measure_fp64_tflops)"}
-        return out
+        gbs = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e9
+        hbm = {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": how,
+               "algorithmic_bytes_per_eval": wl["per_eval"], "dram_bytes_measured": t_bytes, "dram_bytes_source": t_how,
+               "note": "algorithmic bytes / kernel time; not a DRAM utilisation (data and chain state are on chip)"}
+        fpeak = fp64 or 36.0
+        tf = wl["flops_per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak,
+                "traffic": t_bytes, "traffic_source": t_how,
+                "peak_source": "DFMA micro-benchmark in this run (b200_measure_fp64_tflops; MEASURED_PEAKS.json has only HBM "
+                               "and bf16)" if fp64 else "fallback 36.0 (DFMA peak measured on this pool, profiles/)",
+                "algorithmic_flops_per_eval": wl["flops_per_eval"], "kernel": wl["kernel"], "kernel_ms": k_ms,
+                "note": wl["note"], "hbm_by_algorithmic_bytes": hbm}
     # dense contraction on the fp64 tensor path: no fp64 entry in MEASURED_PEAKS.json (HBM + bf16 only), so the
     # denominator is the DMMA rate measured in this process by the library's own micro-benchmark
     peak = dmma or 37.0
     achieved = wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": "fp64 DMMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)"
+            "traffic": t_bytes, "traffic_source": t_how,
+            "peak_source": "fp64 DMMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)"
             if dmma else "fallback 37.0 (scripts/mb/dmma.cu measured on this pool)",
             "kernel": wl["kernel"], "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "note": wl["note"],
             "fp64_dfma_peak_tflops_measured": fp64,
@@ -357,7 +423,7 @@ def b200_arm(args):
 
     def step_device(k):
         return cm.nuts_run(q0_d, states, tune=tune, draws=draws, mean0=mean0_d, store_warmup=False,
-                           philox_seed=1000 + k, device_outputs=True, chain_offset=lo, **run_kw)
+                           philox_seed=1000 + k, device_outputs=True, reuse_outputs=True, chain_offset=lo, **run_kw)
 
     for k in range(args.warmup):
         res = step_device(-1 - k)
@@ -438,20 +504,13 @@ def b200_arm(args):
         if _lib.load().b200_measure_dmma_tflops(ctypes.byref(tf)) == 0:
             dmma = tf.value
     roofline = make_roofline(args.workload, wl, per_launch, k_ms, fp64, dmma, measured_peaks(),
-                             ncu_traffic(per_launch) if args.workload == "radon" else None)
+                             ncu_traffic(args.workload, per_launch))
 
     # ---- cpu_baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import multiprocessing as mp
-
-        procs, threads, chains, ct, cd = cpu_plan(args)
-        with mp.get_context("spawn").Pool(procs) as pool:
-            cpu_run(procs, 2, 1, 999, pool, args.workload, threads)  # import / model-build warm-up
-            e, w, qs = cpu_run(chains, ct, cd, 12345, pool, args.workload, threads)
-        cpu = {"value": e / w, "unit": UNIT, "cores": procs * threads, "kind": "port",
-               "sample": f"{chains} chains x ({ct} tune + {cd} draws) of the same {args.workload} model, {procs} processes x "
-                         f"{threads} BLAS threads", "wall_s": w, "ess": cpu_ess(qs, w)}
+        e, w, ess_c, info, sample, cores = cpu_measure(args, 1)
+        cpu = {"value": e / w, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "wall_s": w, "ess": ess_c, **info}
 
     if rank == 0:
         line = {
@@ -463,6 +522,7 @@ def b200_arm(args):
                        "init": "jitter+adapt_diag" if wl["mass"] == "diag_adapt" else "jitter, fixed dense mass matrix",
                        "momentum": "device philox", "l2": wl["l2"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "host_ms_between_launches": ms_total / args.steps - k_ms,
             "ess": {"min_bulk_ess_last_step": ess_min, "ess_per_sec": ess_min / step_s, "chains": C, "draws": draws},
             "grad_evals_incl_start_state": all_evals * world, "divergent_fraction": div_frac,
         }

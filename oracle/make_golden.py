@@ -172,9 +172,36 @@ def lockstep_cases():
          draws=40, adapt=False, var=a["final_var"], eps=a["final_step_size"])
 
 
+def fullsize_cases():
+    """Goldens for the kernel instantiations the BENCH lines of configs #3 and #5 run:
+    logistic_fused_kernel<16> (K = 128, several chain-CTAs is the test's job) and gemm_nt_dmma_kernel<8|4|2,*> +
+    ls_advance_kernel<16> at n = 10^4.  Short fixed-step replays from a state the reference itself warmed up."""
+    rng = np.random.default_rng(41)
+    args = {"n_rows": 8192, "n_features": 128, "seed": 3}
+    lg = models.logistic(**args)
+    q0s = [lg.initial_point() + rng.uniform(-0.2, 0.2, lg.n) for _ in range(3)]
+    a = case("logistic_k128_adapt", "logistic", args, q0s[:1], [821], tune=120, draws=4, adapt=True)
+    warm = [a["draws_q"][0, -1], a["draws_q"][0, -2], a["draws_q"][0, -3]]
+    case("logistic_k128_fixed", "logistic", args, warm, [822, 823, 824], tune=0, draws=3, adapt=False,
+         var=np.repeat(a["final_var"], 3, axis=0), eps=np.repeat(a["final_step_size"], 3))
+    os.remove(os.path.join(OUT, "logistic_k128_adapt.npz"))  # only the warm state was needed
+    # dense Gaussian at full size: start from draws of the target itself (x = L z), fixed eps, mass = Sigma
+    mv = models.mvgauss()
+    q0s = [mv.data["L"] @ rng.standard_normal(mv.n) for _ in range(2)]
+    case("mvgauss_n10000_fixed", "mvgauss", {}, q0s, [831, 832], tune=0, draws=3, adapt=False, dense=True,
+         eps=np.array([0.15, 0.15]))
+    d = dict(np.load(os.path.join(OUT, "mvgauss_n10000_fixed.npz")))
+    for k in ("var", "init_var", "pre_var", "final_var"):  # unused by a dense-mass replay
+        d[k] = np.zeros(1)
+    np.savez_compressed(os.path.join(OUT, "mvgauss_n10000_fixed.npz"), **d)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lockstep":
         lockstep_cases()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize":
+        fullsize_cases()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "team":
         team_cases()

@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 if (!(P.store_warmup || t >= P.tune)) continue;
                 const int t_o = P.store_warmup ? t : t - P.tune;
                 for (int i = lane; i < n; i += TS) P.draws_out[((long long)chain * T_out + t_o) * n + i] = nan("");
+                if (lane == 0) stats_sentinel(P.st, (long long)chain * T_out + t_o);
             }
         } else {
             S.eps = exp(adapting ? S.log_step : S.log_bar);

@@ -629,6 +629,7 @@ __global__ void B200_NUTS_BOUNDS
                 const int i = lane + TS * k;
                 if (i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = nan("");
             }
+            if (lane == 0) stats_sentinel(P.st, (long long)chain * T_out + t_out);
         }
     }
     // ---- end of run: hand the streams and adaptation results back --------------------------------------

@@ -189,6 +189,9 @@ def convergence_summary(x, large: int = 5_000_000):
                     e.append(ess_bulk_torch(t).cpu())
                     rh.append(rhat_torch(t).cpu())
                 return float(np.nanmin(torch.cat(e).numpy())), float(np.nanmax(torch.cat(rh).numpy()))
-        except Exception:  # any device-side problem: the host path below is always available
-            pass
+        except Exception as e:  # any device-side problem: the host path below is always available, but say so
+            import warnings
+
+            warnings.warn(f"convergence_summary: device path failed ({type(e).__name__}: {e}); falling back to the NumPy "
+                          "estimator, which takes minutes for large posteriors", RuntimeWarning, stacklevel=2)
     return float(np.nanmin(ess_bulk(x))), float(np.nanmax(rhat(x)))

@@ -117,7 +117,7 @@ class CompiledModel:
                  mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
                  k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
-                 device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False):
+                 device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False, reuse_outputs=False):
         """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
 
         ``rng_states``: structured array (``_lib.PCG64_DTYPE``) of the chains' NumPy PCG64 step streams
@@ -125,7 +125,9 @@ class CompiledModel:
         (NumPy ``Generator.normal`` for draw-parity with the reference); otherwise generated on device.
         ``device_outputs=True`` keeps draws/stats as torch CUDA tensors (no D2H copy).
         ``pinned_outputs=True`` returns host arrays backed by a per-model pool of pinned (page-locked) buffers
-        that is REUSED by the next call of the same shape (fast D2H; copy what you want to keep)."""
+        that is REUSED by the next call of the same shape (fast D2H; copy what you want to keep);
+        ``reuse_outputs=True`` does the same for device outputs (no allocator call inside a timed loop).
+        Both are opt-in: the default returns fresh arrays the caller owns."""
         is_torch = lambda a: a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")  # noqa: E731
         if not is_torch(q0):
             q0 = _f64(q0).reshape(-1, self.n)
@@ -148,9 +150,28 @@ class CompiledModel:
         if rng_states.dtype != _lib.PCG64_DTYPE or rng_states.shape != (Cn,):
             raise ValueError("rng_states must be a (chains,) array of _lib.PCG64_DTYPE")
 
-        if device_outputs:
+        tdt = None
+        if device_outputs or pinned_outputs or reuse_outputs:
             import torch
 
+            tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
+        # Output buffers.  The kernels write EVERY element of draws / stats / summary (iterations a frozen chain never ran
+        # get NaN / zero sentinels in-kernel), so buffers are allocated uninitialised and may be reused between calls:
+        # `reuse_outputs` (device) and `pinned_outputs` (host) keep one set per (shape, dtype) in the model handle, which
+        # takes torch's allocator and cudaHostAlloc out of a timed loop.
+        pool = self.__dict__.setdefault("_out_pool", {}) if (reuse_outputs or pinned_outputs) else None
+        counter = [0]
+
+        def pooled(make, shape, dt, space):
+            if pool is None:
+                return make()
+            counter[0] += 1
+            key = (space, counter[0], tuple(shape), np.dtype(dt).str)
+            if key not in pool:
+                pool[key] = make()
+            return pool[key]
+
+        if device_outputs:
             dev = torch.device("cuda", torch.cuda.current_device())
             mem = _lib.MEM_DEVICE
 
@@ -164,10 +185,13 @@ class CompiledModel:
             q0_b, var0_b, mean0_b, z_b = to_dev(q0), to_dev(var0), to_dev(mean0), to_dev(z)
             eps0_b = to_dev(eps0)
             rng_b = torch.as_tensor(rng_states.view(np.uint64).reshape(Cn, 4).view(np.int64), device=dev)
-            draws_b = torch.empty((Cn, T, self.n), dtype=torch.float64, device=dev)  # frozen chains: NaN-filled by the kernel
-            tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
-            mk = lambda shape, dt: torch.zeros(shape, dtype=tdt[dt], device=dev)  # noqa: E731
+            mk = lambda shape, dt: pooled(lambda: torch.empty(shape, dtype=tdt[dt], device=dev), shape, dt, "dev")  # noqa: E731
         else:
+            for a in (q0, var0, mean0, eps0, z):
+                if is_torch(a) and a.is_cuda:
+                    raise ValueError("device_outputs=False takes host (NumPy) inputs; pass device_outputs=True for CUDA tensors")
+            if is_torch(q0):
+                q0 = _f64(q0.numpy()).reshape(-1, self.n)
             mem = _lib.MEM_HOST
             q0_b = q0
             var0_b = None if var0 is None else _f64(var0).reshape(Cn, self.n)
@@ -176,22 +200,11 @@ class CompiledModel:
             eps0_b = None if eps0 is None else np.broadcast_to(_f64(eps0), (Cn,)).copy()
             rng_b = rng_states
             if pinned_outputs:
-                pool = self.__dict__.setdefault("_pinned_pool", {})
-
-                def mk(shape, dt, _tag=[0]):  # noqa: B006
-                    _tag[0] += 1
-                    key = (_tag[0], tuple(shape), np.dtype(dt).str)
-                    if key not in pool:
-                        import torch
-
-                        tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}
-                        pool[key] = torch.zeros(tuple(shape), dtype=tdt[dt], pin_memory=True).numpy()
-                    return pool[key]
-
-                draws_b = mk((Cn, T, self.n), np.float64)
+                mk = lambda shape, dt: pooled(lambda: torch.empty(tuple(shape), dtype=tdt[dt], pin_memory=True).numpy(),  # noqa: E731
+                                              shape, dt, "pin")
             else:
-                draws_b = np.empty((Cn, T, self.n))
-                mk = lambda shape, dt: np.zeros(shape, dtype=dt)  # noqa: E731
+                mk = lambda shape, dt: np.empty(shape, dtype=dt)  # noqa: E731
+        draws_b = mk((Cn, T, self.n), np.float64)
 
         st, st_arr = _lib.Stats(), {}
         if stats:

@@ -29,6 +29,18 @@ def chain_generators(random_seed, chains: int):
     return rngs, pots, jitter_seeds
 
 
+def philox_key(random_seed) -> int:
+    """63-bit key of the device momentum noise (Philox4x32): an independent child of the ROOT seed sequence, on a spawn
+    key no chain stream uses -- full entropy, and not a function of any chain's jitter draws."""
+    if isinstance(random_seed, np.random.Generator):
+        ss = random_seed.bit_generator.seed_seq
+        base = np.random.SeedSequence(ss.entropy, spawn_key=tuple(ss.spawn_key) + (0xB200,))
+    else:
+        base = np.random.SeedSequence(random_seed, spawn_key=(0xB200,))
+    w = base.generate_state(2, dtype=np.uint64)
+    return int(w[0] >> np.uint64(1))
+
+
 def pack_pcg64(generators) -> np.ndarray:
     """NumPy PCG64 Generators -> structured array of (state, inc) split into 64-bit halves."""
     out = np.empty(len(generators), dtype=PCG64_DTYPE)

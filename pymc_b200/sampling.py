@@ -71,7 +71,7 @@ def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, ji
         iv = None
         if initvals is not None:
             iv = initvals[c] if isinstance(initvals, (list, tuple)) else initvals
-        if isinstance(iv, np.ndarray):
+        if isinstance(iv, np.ndarray):  # an explicit raveled start point is used as given (no jitter): parity tests pass these
             q0[c] = iv
             continue
         start = base.copy()
@@ -83,10 +83,14 @@ def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, ji
         q = start
         for _ in range(jitter_max_retries + 1):
             q = start + g.uniform(-1.0, 1.0, spec.n) if jitter else start
-            if logp_fn is None or not jitter:
+            if logp_fn is None:
                 break
             if np.isfinite(logp_fn(q[None])[0][0]):
                 break
+            if not jitter:
+                raise SamplingError(f"Initial evaluation of model at starting point failed for chain {c}: logp is not finite")
+        else:  # _init_jitter raises after jitter_max_retries (pymc/sampling/mcmc.py:1744-1754)
+            raise SamplingError(f"no finite-logp jittered start found for chain {c} after {jitter_max_retries} retries")
         q0[c] = q
     return q0
 
@@ -139,7 +143,8 @@ def sample_b200_nuts(
     mean0 = np.broadcast_to(q0_all.mean(axis=0), (hi - lo, spec.n)).copy()
     states = brng.pack_pcg64(step_rngs[lo:hi])
     z = brng.momentum_noise(pot_rngs[lo:hi], tune + draws, spec.n) if momentum == "numpy" else None
-    seed_key = int(np.random.default_rng(jitter_seeds[0]).integers(2**63)) if z is None else 0
+    # Philox key of the device momentum noise: an independent child of the root seed (never a function of a chain's jitter)
+    seed_key = brng.philox_key(random_seed) if z is None else 0
 
     t0 = time.perf_counter()
     res = cm.nuts_run(q0_all[lo:hi], states, tune=tune, draws=draws, mean0=mean0, z=z, philox_seed=seed_key,

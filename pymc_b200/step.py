@@ -82,6 +82,7 @@ class B200NUTS:
         self.divergences = 0
         self._tune_n = self._draws_n = None
         self._res = None
+        self._base, self._served, self._bad_at, self._resume_eps, self._pot_rng = 0, None, -1, None, None
 
     # ---- BlockedStep protocol (step_methods/compound.py:132-250) -------------------------------------------------
     @staticmethod
@@ -92,12 +93,14 @@ class B200NUTS:
         self.rng = rng
         self._tune_n, self._draws_n = int(tune), int(draws)
         self._res = None
+        self._base, self._served, self._bad_at, self._resume_eps, self._pot_rng = 0, None, -1, None, None
 
     def reset_tuning(self, start=None):
         self.iter_count = 0
         self.divergences = 0
         self.tune = True
         self._res = None
+        self._base, self._served, self._bad_at, self._resume_eps = 0, None, -1, None
 
     def stop_tuning(self):
         if self._tune_n is not None and self.iter_count != self._tune_n and self._res is not None:
@@ -109,36 +112,67 @@ class B200NUTS:
         return np.concatenate([np.ravel(np.asarray(point[v.name], dtype=np.float64)) for v in self.vars])
 
     def _run_chain(self, q0):
+        """Launch the REMAINING schedule of the chain from q0 (iteration ``self.iter_count`` onwards)."""
         from . import rng as brng
 
         if self._tune_n is None:
             raise RuntimeError("setup_chain(rng, tune, draws) must be called before step(): the chain runs as one device launch")
-        T = self._tune_n + self._draws_n
-        tune = self._tune_n if self.tune else 0  # a chain whose tuning was stopped before its first step samples only
+        T = self._tune_n + self._draws_n - self.iter_count
+        if T <= 0:
+            raise RuntimeError("step() called more often than setup_chain announced (tune + draws)")
+        # a chain whose tuning was stopped before this launch samples only
+        tune = max(0, self._tune_n - self.iter_count) if self.tune else 0
         states = brng.pack_pcg64([self.rng])
         z, seed = None, 0
         if self._momentum == "numpy":
-            z = brng.momentum_noise([self.rng.spawn(1)[0]], T, self.spec.n)
+            if self._pot_rng is None:
+                self._pot_rng = self.rng.spawn(1)[0]  # hmc/base_hmc.py:300-302
+            z = brng.momentum_noise([self._pot_rng], T, self.spec.n)
         else:
             seed = int(self.rng.spawn(1)[0].integers(2**63))
+        kw = dict(self._kw)
+        eps0 = None
+        if self._resume_eps is not None:  # re-launch mid-chain: continue from the step size adapted so far
+            eps0 = np.array([self._resume_eps])
         self._res = self._cm.nuts_run(q0[None, :], states, tune=tune, draws=T - tune, z=z, philox_seed=seed, store_warmup=True,
-                                      mass="diag_adapt", mean0=self._mean0[None, :], var0=self._var0[None, :], **self._kw)
+                                      mass="diag_adapt", mean0=self._mean0[None, :], var0=self._var0[None, :], eps0=eps0, **kw)
+        self._base = self.iter_count
+        self._served = q0.copy()
         brng.unpack_pcg64(states, [self.rng])  # the host generator continues where the device stopped
-        if int(self._res.summary["bad_energy_at"][0]) >= 0:
-            from .sampling import SamplingError
-
-            raise SamplingError(f"Bad initial energy at iteration {int(self._res.summary['bad_energy_at'][0])}")
+        self._bad_at = int(self._res.summary["bad_energy_at"][0])
 
     def step(self, point):
         import time
 
         t0 = time.perf_counter()
+        q_in = self._ravel(point)
+        if self._res is not None and not np.array_equal(q_in, self._served):
+            # BaseHMC.astep re-reads q0 on every call (hmc/base_hmc.py:196-202).  The chain was run ahead from the point
+            # of the previous call; a driver that changed the point in between (CompoundStep with other step methods,
+            # hand-written loops) gets a fresh launch of the remaining schedule from ITS point, never stale draws.
+            import warnings
+
+            warnings.warn("B200NUTS.step: the incoming point differs from the previously returned draw; re-launching the "
+                          "remaining schedule from it (mass-matrix adaptation restarts, the step size carries over)",
+                          RuntimeWarning, stacklevel=2)
+            i_prev = self.iter_count - self._base - 1
+            if i_prev >= 0:
+                key = "step_size" if self.tune else "step_size_bar"
+                self._resume_eps = float(self._res.stats[key][0, i_prev])
+            self._res = None
         if self._res is None:
-            self._run_chain(self._ravel(point))
-        i = self.iter_count
+            self._run_chain(q_in)
+        i = self.iter_count - self._base
         if i >= np.asarray(self._res.draws).shape[1]:
             raise RuntimeError("step() called more often than setup_chain announced (tune + draws)")
+        if self._bad_at >= 0 and i >= self._bad_at:
+            # raised at the iteration where the reference raises it (base_hmc.py:205-224), after the valid draws before it
+            from .sampling import SamplingError
+
+            raise SamplingError(f"Bad initial energy at iteration {self.iter_count}: check any log probabilities that are "
+                                "inf or nan (model.debug())")
         q = np.asarray(self._res.draws[0, i])
+        self._served = q.copy()
         st = {k: v[0, i] for k, v in self._res.stats.items()}
         diverging = bool(st["diverging"])
         if not self.tune:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200NUTS_VERSION 100 /* 0.1.0 */
+#define B200NUTS_VERSION 200 /* 0.2.0: b200_model_desc.ir (ModelSpec IR), appended at the end of the struct */
 
 /* memory space of caller-provided buffers */
 #define B200_MEM_HOST 0
@@ -47,6 +47,84 @@ extern "C" {
 #define B200_MODEL_LOGISTIC 3      /* BASELINE config 3, beta~N(0,1), y~Bernoulli(logit_p=X beta)   */
 #define B200_MODEL_STOCHVOL 4      /* BASELINE config 4, AR(1) stochastic volatility               */
 #define B200_MODEL_MVGAUSS 5       /* BASELINE config 5, x~MvNormal(0, chol=L), dense mass matrix   */
+#define B200_MODEL_IR 6            /* any model of the closed factor set below (b200_ir): ONE generic fused logp+gradient
+                                    * device function (csrc/ir_model.cuh), no new CUDA per model.  The kinds above are
+                                    * hand-specialised fast paths that pymc_b200.ir.specialise() routes matching IR to. */
+
+/* ---- ModelSpec IR: what Model.logp_dlogp_function closes over, as data --------------------------------------------------
+ * Ordered value variables with their transforms (pymc/logprob/transforms.py:880-891 log, :1026-1073 interval), and a list
+ * of factors whose log-densities are summed (pymc/model/core.py:688-690).  All pointers are HOST memory, copied at create.
+ * Parameters are constants or SCALAR value variables seen through their transform (hierarchical priors). */
+#define B200_IR_T_NONE 0
+#define B200_IR_T_LOG 1
+#define B200_IR_T_INTERVAL 2
+/* prior densities (pymc/distributions/continuous.py): parameters in p[0..2] */
+#define B200_IR_P_FLAT 0        /*                       :364-419   */
+#define B200_IR_P_NORMAL 1      /* mu, sigma             :526-527   */
+#define B200_IR_P_HALFNORMAL 2  /* sigma                 :909-911   */
+#define B200_IR_P_CAUCHY 3      /* alpha, beta           :2287-2288 */
+#define B200_IR_P_HALFCAUCHY 4  /* beta                  :2383-2385 */
+#define B200_IR_P_EXPONENTIAL 5 /* lam                   :1478-1480 */
+#define B200_IR_P_STUDENTT 6    /* nu (const), mu, sigma :1936-1944 */
+#define B200_IR_P_UNIFORM 7     /* lower, upper (const)  :309-314   */
+#define B200_IR_P_GAMMA 8       /* alpha, beta (const)   :2512-2515 */
+#define B200_IR_P_BETA 9        /* alpha, beta (const)   :1250-1256 */
+#define B200_IR_P_LOGNORMAL 10  /* mu, sigma             :1807-1814 */
+/* likelihoods of a linear predictor eta_i = sum_t coef_t[i] * prod_f x_f[idx_f[i]] */
+#define B200_IR_L_NORMAL 0          /* y ~ Normal(eta, sigma)                    continuous.py:526-527  */
+#define B200_IR_L_BERNOULLI_LOGIT 1 /* y ~ Bernoulli(logit_p = eta)              discrete.py:362-367    */
+#define B200_IR_L_POISSON_LOG 2     /* y ~ Poisson(exp(eta))                     discrete.py:581-586    */
+#define B200_IR_L_STUDENTT 3        /* y ~ StudentT(nu, eta, sigma)              continuous.py:1936-1944 */
+#define B200_IR_L_NORMAL_LOGVAR 4   /* y ~ Normal(0, exp(eta / 2))                                      */
+#define B200_IR_S_NONE 0
+#define B200_IR_S_CONST 1 /* sigma.value               */
+#define B200_IR_S_REF 2   /* sigma = x[sigma.ref]      */
+#define B200_IR_S_OBS 3   /* sigma_obs[N] (known per-observation scale) */
+
+typedef struct b200_ir_param {
+    int32_t kind;  /* 0: constant `value`; 1: the constrained value of the scalar variable at offset `ref` of q */
+    int32_t ref;
+    double value;
+} b200_ir_param;
+typedef struct b200_ir_var {
+    int32_t offset, size, transform, reserved;
+    double lo, hi; /* interval bounds */
+} b200_ir_var;
+typedef struct b200_ir_prior {
+    int32_t dist, var; /* var: index into vars */
+    b200_ir_param p[3];
+} b200_ir_prior;
+typedef struct b200_ir_factor {
+    int32_t offset, size; /* the variable's slice of q */
+    const int32_t* idx;   /* [N] gather index into the variable, or NULL (scalar: broadcast; size == N: elementwise) */
+} b200_ir_factor;
+typedef struct b200_ir_term {
+    const double* coef; /* [N] or NULL (= 1) */
+    int32_t n_factors, reserved;
+    b200_ir_factor f[3];
+} b200_ir_term;
+typedef struct b200_ir_lik {
+    int32_t dist, n_terms;
+    int64_t N;
+    const double* y; /* [N] */
+    const b200_ir_term* terms;
+    int32_t sigma_kind, reserved;
+    b200_ir_param sigma;
+    const double* sigma_obs; /* [N] when sigma_kind == B200_IR_S_OBS */
+    double nu;
+} b200_ir_lik;
+typedef struct b200_ir_ar1 { /* h_0 ~ Normal(0, init_sigma); h_t - phi h_{t-1} ~ Normal(0, sigma)  (timeseries.py:646-676) */
+    int32_t var, reserved;
+    b200_ir_param phi, sigma;
+    double init_sigma;
+} b200_ir_ar1;
+typedef struct b200_ir {
+    int32_t n_vars, n_priors, n_liks, n_ar1;
+    const b200_ir_var* vars;
+    const b200_ir_prior* priors;
+    const b200_ir_lik* liks;
+    const b200_ir_ar1* ar1;
+} b200_ir;
 
 /* mass-matrix kinds (reference: pymc/step_methods/hmc/quadpotential.py) */
 #define B200_MASS_DIAG 0       /* QuadPotentialDiag      :582-630  (fixed diagonal)                   */
@@ -75,6 +153,7 @@ typedef struct b200_model_desc {
     double scalar0;      /* MVGAUSS: sum(log diag L) (constant of the log-density)                    */
     const double* m1;    /* MVGAUSS: L^-T [n][n] row-major (p0 = solve_triangular(L^T, z) = L^-T z)   */
     const double* m2;    /* MVGAUSS: Cholesky factor L [n][n] row-major (v0 = Sigma p0 = L z)         */
+    const b200_ir* ir;   /* IR: the model as data (see above)                                         */
 } b200_model_desc;
 
 /* NumPy PCG64 stream state (numpy.random.PCG64().state["state"]): 128-bit LCG state and increment.
@@ -137,6 +216,11 @@ typedef struct b200_chain_summary {
 
 int b200_version(void);
 const char* b200_last_error(void);
+/* sizeof() of the ABI structs as this library was compiled, so a host binding can verify its mirrors before passing
+ * pointers: which = 0 b200_model_desc, 1 b200_nuts_cfg, 2 b200_stats, 3 b200_chain_summary, 4 b200_pcg64, 5 b200_ir,
+ * 6 b200_ir_var, 7 b200_ir_prior, 8 b200_ir_term, 9 b200_ir_lik, 10 b200_ir_ar1, 11 b200_ir_param, 12 b200_ir_factor;
+ * -1 for an unknown index. */
+int b200_struct_size(int which);
 
 /* Number of visible CUDA devices (0 if none / no driver): lets a host binding fail loudly. */
 int b200_device_count(void);

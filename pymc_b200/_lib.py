@@ -36,7 +36,95 @@ class ModelDesc(C.Structure):
         ("scalar0", C.c_double),
         ("m1", C.c_void_p),
         ("m2", C.c_void_p),
+        ("ir", C.c_void_p),
     ]
+
+
+# ---- ModelSpec IR (include/b200nuts.h: b200_ir_*) ---------------------------------------------------------------------
+MODEL_IR = 6
+
+
+class IrParam(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ref", C.c_int32), ("value", C.c_double)]
+
+
+class IrVar(C.Structure):
+    _fields_ = [("offset", C.c_int32), ("size", C.c_int32), ("transform", C.c_int32), ("reserved", C.c_int32),
+                ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class IrPrior(C.Structure):
+    _fields_ = [("dist", C.c_int32), ("var", C.c_int32), ("p", IrParam * 3)]
+
+
+class IrFactor(C.Structure):
+    _fields_ = [("offset", C.c_int32), ("size", C.c_int32), ("idx", C.c_void_p)]
+
+
+class IrTerm(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("n_factors", C.c_int32), ("reserved", C.c_int32), ("f", IrFactor * 3)]
+
+
+class IrLik(C.Structure):
+    _fields_ = [("dist", C.c_int32), ("n_terms", C.c_int32), ("N", C.c_int64), ("y", C.c_void_p), ("terms", C.c_void_p),
+                ("sigma_kind", C.c_int32), ("reserved", C.c_int32), ("sigma", IrParam), ("sigma_obs", C.c_void_p),
+                ("nu", C.c_double)]
+
+
+class IrAr1(C.Structure):
+    _fields_ = [("var", C.c_int32), ("reserved", C.c_int32), ("phi", IrParam), ("sigma", IrParam), ("init_sigma", C.c_double)]
+
+
+class Ir(C.Structure):
+    _fields_ = [("n_vars", C.c_int32), ("n_priors", C.c_int32), ("n_liks", C.c_int32), ("n_ar1", C.c_int32),
+                ("vars", C.c_void_p), ("priors", C.c_void_p), ("liks", C.c_void_p), ("ar1", C.c_void_p)]
+
+
+def build_ir(low):
+    """pymc_b200.ir.LoweredIR -> (ctypes b200_ir, keep-alive list).  Pointers reference NumPy arrays held in `keep`."""
+    keep = []
+
+    def param(t):
+        kind, value, ref = t
+        return IrParam(int(kind), int(ref), float(value))
+
+    def addr(a):
+        if a is None:
+            return None
+        keep.append(a)
+        return a.ctypes.data
+
+    nv = len(low.vars)
+    vars_ = (IrVar * nv)()
+    for k in range(nv):
+        o, sz, tr = (int(x) for x in low.vars[k])
+        vars_[k] = IrVar(o, sz, tr, 0, float(low.var_bounds[k][0]), float(low.var_bounds[k][1]))
+    pri = (IrPrior * max(1, len(low.priors)))()
+    for k, (dist, var, pars) in enumerate(low.priors):
+        pri[k].dist, pri[k].var = int(dist), int(var)
+        for a in range(3):
+            pri[k].p[a] = param(pars[a])
+    liks = (IrLik * max(1, len(low.liks)))()
+    for k, L in enumerate(low.liks):
+        terms = (IrTerm * len(L["terms"]))()
+        for t, T in enumerate(L["terms"]):
+            terms[t].coef = addr(T["coef"])
+            terms[t].n_factors = len(T["factors"])
+            for f, (o, sz, idx) in enumerate(T["factors"]):
+                terms[t].f[f] = IrFactor(int(o), int(sz), addr(idx))
+        keep.append(terms)
+        liks[k].dist, liks[k].n_terms, liks[k].N = int(L["dist"]), len(L["terms"]), int(L["N"])
+        liks[k].y, liks[k].terms = addr(L["y"]), C.addressof(terms)
+        liks[k].sigma_kind = int(L["sigma_kind"])
+        liks[k].sigma = IrParam(1 if L["sigma_kind"] == 2 else 0, int(L["sigma_ref"]), float(L["sigma_value"]))
+        liks[k].sigma_obs, liks[k].nu = addr(L["sigma_obs"]), float(L["nu"])
+    ars = (IrAr1 * max(1, len(low.ar1)))()
+    for k, (var, phi, sigma, init_sigma) in enumerate(low.ar1):
+        ars[k].var, ars[k].phi, ars[k].sigma, ars[k].init_sigma = int(var), param(phi), param(sigma), float(init_sigma)
+    ir = Ir(nv, len(low.priors), len(low.liks), len(low.ar1), C.addressof(vars_), C.addressof(pri), C.addressof(liks),
+            C.addressof(ars))
+    keep += [vars_, pri, liks, ars]
+    return ir, keep
 
 
 class Pcg64State(C.Structure):
@@ -107,6 +195,7 @@ class ChainSummary(C.Structure):
 SYMBOLS = [
     ("b200_version", C.c_int, []),
     ("b200_last_error", C.c_char_p, []),
+    ("b200_struct_size", C.c_int, [C.c_int]),
     ("b200_device_count", C.c_int, []),
     ("b200_set_device", C.c_int, [C.c_int]),
     ("b200_model_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
@@ -139,9 +228,16 @@ def load() -> C.CDLL:
             raise B200Error(f"{LIB_PATH} is missing: build the CUDA engine first (./build.sh); there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)
         for name, restype, argtypes in SYMBOLS:
+            if name == "b200_struct_size" and not hasattr(lib, name):
+                continue  # an A/B build (B200_LIB=...) older than ABI 0.2.0; tests/test_abi.py requires it of the in-tree library
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
+        mirrors = [ModelDesc, NutsCfg, Stats, ChainSummary, Pcg64State, Ir, IrVar, IrPrior, IrTerm, IrLik, IrAr1, IrParam, IrFactor]
+        for which, cls in enumerate(mirrors if hasattr(lib, "b200_struct_size") else []):
+            if lib.b200_struct_size(which) != C.sizeof(cls):
+                raise B200Error(f"ABI mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, {lib.b200_struct_size(which)} in "
+                                f"{LIB_PATH} (rebuild with ./build.sh)")
         _lib = lib
     return _lib
 

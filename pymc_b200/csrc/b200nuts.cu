@@ -6,12 +6,15 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dense.cuh"
+#include "ir_model.cuh"
 #include "lockstep.cuh"
 #include "models.cuh"
 #include "nuts_warp.cuh"
@@ -55,6 +58,23 @@ struct b200_model {
     EightSchoolsModel::Params eight{};
     RadonModel::Params radon{};
     StochVolModel::Params stochvol{};
+    IrModel::Params ir{};
+    long long ir_max_obs = 0;
+    void* ir_scratch = nullptr;   // per-team scratch of the generic IR device function: [slots][n_pad + max N] doubles
+    size_t ir_scratch_bytes = 0;
+    cudaError_t ensure_ir_scratch(long long slots) {
+        const size_t bytes = (size_t)slots * (size_t)ir.stride * sizeof(double);
+        if (bytes > ir_scratch_bytes) {
+            if (ir_scratch) cudaFree(ir_scratch);
+            ir_scratch = nullptr;
+            ir_scratch_bytes = 0;
+            cudaError_t e = cudaMalloc(&ir_scratch, bytes);
+            if (e != cudaSuccess) return e;
+            ir_scratch_bytes = bytes;
+        }
+        ir.scratch = static_cast<double*>(ir_scratch);
+        return cudaSuccess;
+    }
     // lock-step (GEMM-shaped) models; every matrix is row-major with rows `ld` doubles apart (n rounded up to 4, zero pad)
     long long ld = 0;
     const double* prec = nullptr;   // MVGAUSS: precision P [n][ld]
@@ -80,6 +100,7 @@ struct b200_model {
         return e;
     }
     ~b200_model() {
+        if (ir_scratch) cudaFree(ir_scratch);
         if (scratch) cudaFree(scratch);
         for (void* p : owned) cudaFree(p);
     }
@@ -100,6 +121,24 @@ static int upload(b200_model* m, const std::vector<T>& h, const T** out) {
 
 extern "C" int b200_version(void) { return B200NUTS_VERSION; }
 extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(b200_model_desc);
+        case 1: return (int)sizeof(b200_nuts_cfg);
+        case 2: return (int)sizeof(b200_stats);
+        case 3: return (int)sizeof(b200_chain_summary);
+        case 4: return (int)sizeof(b200_pcg64);
+        case 5: return (int)sizeof(b200_ir);
+        case 6: return (int)sizeof(b200_ir_var);
+        case 7: return (int)sizeof(b200_ir_prior);
+        case 8: return (int)sizeof(b200_ir_term);
+        case 9: return (int)sizeof(b200_ir_lik);
+        case 10: return (int)sizeof(b200_ir_ar1);
+        case 11: return (int)sizeof(b200_ir_param);
+        case 12: return (int)sizeof(b200_ir_factor);
+        default: return -1;
+    }
+}
 
 extern "C" int b200_device_count(void) {
     int n = 0;
@@ -242,6 +281,154 @@ static int prepare_logistic(b200_model* m, const b200_model_desc* d) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ModelSpec IR -> device tables (csrc/ir_model.cuh).  Validates the closed set, precomputes the constant parts of the
+// densities on the host (lgamma, log 2pi ...) and builds, for every indexed factor, the CSR transpose of its gather index
+// (element -> observations) that the gradient is pulled through (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+static int ir_param(const b200_ir_param& p, int n, IrParamD* out, const char* what) {
+    if (p.kind != 0 && p.kind != 1) return fail("ir: %s: parameter kind %d", what, p.kind);
+    if (p.kind == 1 && (p.ref < 0 || p.ref >= n)) return fail("ir: %s: parameter reference %d outside q[0..%d)", what, p.ref, n);
+    out->kind = p.kind; out->ref = p.kind ? p.ref : 0; out->value = p.value;
+    return 0;
+}
+
+static int prepare_ir(b200_model* m, const b200_model_desc* d) {
+    const b200_ir* R = d->ir;
+    if (!R) return fail("ir: desc.ir is null");
+    if (R->n_vars <= 0 || !R->vars) return fail("ir: no value variables");
+    const int n = d->n;
+    std::vector<IrVarD> vars(R->n_vars);
+    int off = 0;
+    for (int v = 0; v < R->n_vars; ++v) {
+        const b200_ir_var& V = R->vars[v];
+        if (V.offset != off || V.size <= 0) return fail("ir: variable %d: offsets must be contiguous in registration order", v);
+        if (V.transform < B200_IR_T_NONE || V.transform > B200_IR_T_INTERVAL) return fail("ir: variable %d: transform %d", v, V.transform);
+        if (V.transform == B200_IR_T_INTERVAL && !(V.lo < V.hi)) return fail("ir: variable %d: interval needs lo < hi", v);
+        vars[v] = IrVarD{V.offset, V.size, V.transform, 0, V.lo, V.hi};
+        off += V.size;
+    }
+    if (off != n) return fail("ir: variables cover %d elements but n = %d", off, n);
+    const double LOG_PI = 1.1447298858494001741, LOG_2 = 0.69314718055994530942;
+    std::vector<IrPriorD> priors(std::max(R->n_priors, 0));
+    for (int k = 0; k < R->n_priors; ++k) {
+        const b200_ir_prior& F = R->priors[k];
+        if (F.var < 0 || F.var >= R->n_vars) return fail("ir: prior %d: variable index %d", k, F.var);
+        IrPriorD P{};
+        P.dist = F.dist; P.offset = vars[F.var].offset; P.size = vars[F.var].size;
+        for (int a = 0; a < 3; ++a)
+            if (ir_param(F.p[a], n, &P.p[a], "prior")) return -1;
+        auto cst = [&](int a) { return F.p[a].kind == 0; };
+        switch (F.dist) {
+            case B200_IR_P_FLAT: break;
+            case B200_IR_P_NORMAL: case B200_IR_P_LOGNORMAL: P.c0 = -B200_HALF_LOG_2PI; break;
+            case B200_IR_P_HALFNORMAL: P.c0 = 0.5 * (LOG_2 - LOG_PI); break;
+            case B200_IR_P_CAUCHY: P.c0 = -LOG_PI; break;
+            case B200_IR_P_HALFCAUCHY: P.c0 = LOG_2 - LOG_PI; break;
+            case B200_IR_P_EXPONENTIAL: break;
+            case B200_IR_P_STUDENTT: {
+                if (!cst(0) || !(F.p[0].value > 0)) return fail("ir: prior %d: StudentT nu must be a positive constant", k);
+                const double nu = F.p[0].value;
+                P.c0 = std::lgamma(0.5 * (nu + 1.0)) - std::lgamma(0.5 * nu) - 0.5 * std::log(nu) - 0.5 * LOG_PI;
+            } break;
+            case B200_IR_P_UNIFORM:
+                if (!cst(0) || !cst(1) || !(F.p[0].value < F.p[1].value)) return fail("ir: prior %d: Uniform bounds must be constants lo < hi", k);
+                P.c0 = -std::log(F.p[1].value - F.p[0].value);
+                break;
+            case B200_IR_P_GAMMA:
+                if (!cst(0) || !cst(1) || !(F.p[0].value > 0) || !(F.p[1].value > 0)) return fail("ir: prior %d: Gamma needs constant alpha, beta > 0", k);
+                P.c0 = F.p[0].value * std::log(F.p[1].value) - std::lgamma(F.p[0].value);
+                break;
+            case B200_IR_P_BETA:
+                if (!cst(0) || !cst(1) || !(F.p[0].value > 0) || !(F.p[1].value > 0)) return fail("ir: prior %d: Beta needs constant alpha, beta > 0", k);
+                P.c0 = -(std::lgamma(F.p[0].value) + std::lgamma(F.p[1].value) - std::lgamma(F.p[0].value + F.p[1].value));
+                break;
+            default: return fail("ir: prior %d: density %d is not in the closed set", k, F.dist);
+        }
+        priors[k] = P;
+    }
+    std::vector<IrLikD> liks(std::max(R->n_liks, 0));
+    std::vector<IrTermD> terms;
+    long long max_obs = 0;
+    for (int l = 0; l < R->n_liks; ++l) {
+        const b200_ir_lik& L = R->liks[l];
+        if (L.N <= 0 || L.N > 0x7fffffff || !L.y) return fail("ir: likelihood %d: missing observations", l);
+        if (L.n_terms <= 0 || !L.terms) return fail("ir: likelihood %d: no linear-predictor terms", l);
+        const long long N = L.N;
+        max_obs = std::max(max_obs, N);
+        IrLikD D{};
+        D.dist = L.dist; D.n_terms = L.n_terms; D.term0 = (int)terms.size(); D.sigma_kind = L.sigma_kind; D.N = N; D.nu = L.nu;
+        if (upload_raw(m, L.y, (size_t)N, &D.y)) return -1;
+        if (ir_param(L.sigma, n, &D.sigma, "likelihood sigma")) return -1;
+        if (L.sigma_kind == B200_IR_S_REF && L.sigma.kind != 1) return fail("ir: likelihood %d: sigma_kind REF needs a reference", l);
+        if (L.sigma_kind == B200_IR_S_OBS) {
+            if (!L.sigma_obs) return fail("ir: likelihood %d: sigma_obs missing", l);
+            if (upload_raw(m, L.sigma_obs, (size_t)N, &D.sigma_obs)) return -1;
+        }
+        switch (L.dist) {
+            case B200_IR_L_NORMAL: case B200_IR_L_NORMAL_LOGVAR: D.c0 = -(double)N * B200_HALF_LOG_2PI; break;
+            case B200_IR_L_BERNOULLI_LOGIT: break;
+            case B200_IR_L_POISSON_LOG: { double c = 0; for (long long i = 0; i < N; ++i) c -= std::lgamma(L.y[i] + 1.0); D.c0 = c; } break;
+            case B200_IR_L_STUDENTT:
+                if (!(L.nu > 0)) return fail("ir: likelihood %d: StudentT nu must be > 0", l);
+                D.c0 = (double)N * (std::lgamma(0.5 * (L.nu + 1.0)) - std::lgamma(0.5 * L.nu) - 0.5 * std::log(L.nu) - 0.5 * LOG_PI);
+                break;
+            default: return fail("ir: likelihood %d: density %d is not in the closed set", l, L.dist);
+        }
+        if ((L.dist == B200_IR_L_NORMAL || L.dist == B200_IR_L_STUDENTT) && L.sigma_kind == B200_IR_S_NONE)
+            return fail("ir: likelihood %d needs sigma", l);
+        for (int t = 0; t < L.n_terms; ++t) {
+            const b200_ir_term& T = L.terms[t];
+            if (T.n_factors < 1 || T.n_factors > 3) return fail("ir: likelihood %d term %d: 1..3 variable factors", l, t);
+            IrTermD TD{};
+            TD.n_factors = T.n_factors;
+            if (T.coef && upload_raw(m, T.coef, (size_t)N, &TD.coef)) return -1;
+            for (int f = 0; f < T.n_factors; ++f) {
+                const b200_ir_factor& F = T.f[f];
+                if (F.offset < 0 || F.size <= 0 || F.offset + F.size > n) return fail("ir: likelihood %d term %d: factor slice outside q", l, t);
+                IrFactorD FD{};
+                FD.offset = F.offset; FD.size = F.size;
+                if (F.idx) {
+                    std::vector<int> rowptr(F.size + 1, 0), rowobs((size_t)N);
+                    for (long long i = 0; i < N; ++i) {
+                        if (F.idx[i] < 0 || F.idx[i] >= F.size) return fail("ir: likelihood %d term %d: index %d out of range at %lld", l, t, F.idx[i], i);
+                        ++rowptr[F.idx[i] + 1];
+                    }
+                    for (int j = 0; j < F.size; ++j) rowptr[j + 1] += rowptr[j];
+                    std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+                    for (long long i = 0; i < N; ++i) rowobs[fill[F.idx[i]]++] = (int)i;  // ascending i inside a row: fixed order
+                    if (upload_raw(m, F.idx, (size_t)N, &FD.idx) || upload(m, rowptr, &FD.rowptr) || upload(m, rowobs, &FD.rowobs)) return -1;
+                } else if (F.size != 1 && F.size != N) {
+                    return fail("ir: likelihood %d term %d: a variable of size %d needs an index to enter %lld observations", l, t, F.size, N);
+                }
+                TD.f[f] = FD;
+            }
+            terms.push_back(TD);
+        }
+        liks[l] = D;
+    }
+    std::vector<IrAr1D> ars(std::max(R->n_ar1, 0));
+    for (int k = 0; k < R->n_ar1; ++k) {
+        const b200_ir_ar1& A = R->ar1[k];
+        if (A.var < 0 || A.var >= R->n_vars || vars[A.var].size < 2) return fail("ir: ar1 %d: bad variable", k);
+        if (!(A.init_sigma > 0)) return fail("ir: ar1 %d: init_sigma must be > 0", k);
+        IrAr1D D{};
+        D.offset = vars[A.var].offset; D.size = vars[A.var].size; D.init_sigma = A.init_sigma;
+        if (ir_param(A.phi, n, &D.phi, "ar1 phi") || ir_param(A.sigma, n, &D.sigma, "ar1 sigma")) return -1;
+        ars[k] = D;
+    }
+    IrModel::Params& P = m->ir;
+    P.n_vars = R->n_vars; P.n_priors = (int)priors.size(); P.n_liks = (int)liks.size(); P.n_ar1 = (int)ars.size(); P.n = n;
+    if (upload(m, vars, &P.vars) || upload(m, priors, &P.priors) || upload(m, liks, &P.liks) || upload(m, terms, &P.terms) ||
+        upload(m, ars, &P.ar1))
+        return -1;
+    P.n_pad = (n + 3) & ~3;
+    P.stride = P.n_pad + ((max_obs + 3) & ~3LL);
+    m->ir_max_obs = max_obs;
+    return 0;
+}
+
 extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) {
     if (!desc || !out) return fail("b200_model_create: null argument");
     if (desc->n <= 0) return fail("b200_model_create: n must be positive");
@@ -258,6 +445,7 @@ extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) 
         case B200_MODEL_STOCHVOL: rc = prepare_stochvol(m, desc); break;
         case B200_MODEL_MVGAUSS: rc = prepare_mvgauss(m, desc); break;
         case B200_MODEL_LOGISTIC: rc = prepare_logistic(m, desc); break;
+        case B200_MODEL_IR: rc = prepare_ir(m, desc); break;
         default: rc = fail("b200_model_create: model kind %d not implemented", desc->kind);
     }
     if (rc) {
@@ -331,10 +519,29 @@ static int dispatch(const b200_model* m, F&& f) {
         case B200_MODEL_STOCHVOL:
             B200_TEAM(StochVolModel, m->stochvol)
             return fail("stochvol: n=%d exceeds 4096", m->n);
+        case B200_MODEL_IR:
+            if (m->n <= 256 && !env_flag("B200_FORCE_TEAM")) { B200_WARP(IrModel, m->ir) }
+            B200_TEAM(IrModel, m->ir)
+            return fail("ir: n=%d exceeds the chain-per-CTA limit (4096)", m->n);
     }
 #undef B200_WARP
 #undef B200_TEAM
     return fail("dispatch: model kind %d not implemented", m->kind);
+}
+
+
+// The generic IR device function keeps x (constrained values) and the per-observation residuals of the likelihood being
+// processed in a per-team global scratch slice: size it for the launch (teams = CTAs x teams per CTA) and hand the kernel
+// the Params copy that points at it.
+template <class Model>
+static int launch_params(const b200_model* m, const typename Model::Params& MP, long long teams, typename Model::Params* out) {
+    *out = MP;
+    if constexpr (std::is_same_v<Model, IrModel>) {
+        b200_model* mm = const_cast<b200_model*>(m);
+        CU(mm->ensure_ir_scratch(teams));
+        *out = mm->ir;
+    }
+    return 0;
 }
 
 struct Timer {
@@ -414,7 +621,9 @@ struct LogpLaunch {
         auto kern = logp_grad_warp_kernel<Model, NPL, W>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
-        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MP, m->n, C, q, logp, grad);
+        typename Model::Params MPl;
+        if (launch_params<Model>(m, MP, (long long)blocks * wpb, &MPl)) return -1;
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MPl, m->n, C, q, logp, grad);
         CU(cudaGetLastError());
         return 0;
     }
@@ -458,7 +667,9 @@ struct LeapLaunch {
         auto kern = leapfrog_warp_kernel<Model, NPL, W>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
-        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MP, m->n, C, var, eps, n_steps, q, p, v, grad, energy, logp, idx);
+        typename Model::Params MPl;
+        if (launch_params<Model>(m, MP, (long long)blocks * wpb, &MPl)) return -1;
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MPl, m->n, C, var, eps, n_steps, q, p, v, grad, energy, logp, idx);
         CU(cudaGetLastError());
         return 0;
     }
@@ -702,13 +913,36 @@ struct NutsLaunch {
         if (smem > 227 * 1024) return fail("nuts: shared memory request %zu B exceeds 227 KB", smem);
         P.hot_levels = hot;
         P.scratch_stride = nuts_scratch_doubles(NP, P.max_td);
-        CU(m->ensure_scratch((size_t)P.C * P.scratch_stride * sizeof(double)));
-        P.scratch = static_cast<double*>(m->scratch);
+        // tree scratch [C][stride] | ChainCtx [C] | done [C] | ticket
+        const size_t tree_bytes = ((size_t)P.C * P.scratch_stride * sizeof(double) + 255) & ~(size_t)255;
+        const size_t ctx_bytes = ((size_t)P.C * sizeof(ChainCtx) + 255) & ~(size_t)255;
+        const size_t sched_bytes = ((size_t)(P.C + 1) * sizeof(int) + 255) & ~(size_t)255;
+        CU(m->ensure_scratch(tree_bytes + ctx_bytes + sched_bytes));
+        char* base = static_cast<char*>(m->scratch);
+        P.scratch = reinterpret_cast<double*>(base);
+        P.ctx = reinterpret_cast<ChainCtx*>(base + tree_bytes);
+        P.done = reinterpret_cast<int*>(base + tree_bytes + ctx_bytes);
+        P.ticket = reinterpret_cast<unsigned int*>(P.done + P.C);
+        CU(cudaMemsetAsync(P.done, 0, sched_bytes, st));
         auto kern = nuts_warp_kernel<Model, NPL, W, SUBS>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int blocks = (P.C + wpb - 1) / wpb;
+        // persistent grid: every CTA resident (teams take (chain, segment) units from the ticket counter)
+        const int threads = (W == 1) ? wpb * 32 : 32 * W;
+        int per_sm = 0, sms = 148;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+        const int need = (P.C + wpb - 1) / wpb;
+        const int blocks = std::max(1, std::min(need, std::max(1, per_sm) * sms));
+        // iterations per work unit: fine enough to balance chains of different cost, coarse enough that the ~3 KB state
+        // hand-over per unit is noise.  One unit per chain when every chain has its own resident team anyway.
+        const int Ttot = P.tune + P.draws;
+        int seg = env_int("B200_NUTS_SEG", 25);
+        if (seg <= 0 || need <= blocks) seg = Ttot;
+        P.seg_iters = std::max(1, std::min(seg, Ttot));
+        typename Model::Params MPl;
+        if (launch_params<Model>(m, MP, (long long)blocks * wpb, &MPl)) return -1;
         Timer t(st);
-        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(P, MP);
+        kern<<<blocks, threads, smem, st>>>(P, MPl);
         CU(cudaGetLastError());
         t.stop(1);
         CU(cudaStreamSynchronize(st));

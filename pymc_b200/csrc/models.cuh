@@ -16,11 +16,6 @@
 
 namespace b200 {
 
-#ifndef B200_RADON_SMALL_UNROLL
-#define B200_RADON_SMALL_UNROLL 1  // untested candidate: 2 (ping-pong of the prefetch registers, no register moves)
-#endif
-constexpr int kRadonSmallUnroll = B200_RADON_SMALL_UNROLL;
-
 // ------------------------------------------------------------------------------------------------
 // x ~ Normal(0,1)^n  (test model; Normal.logp distributions/continuous.py:526-527)
 // ------------------------------------------------------------------------------------------------
@@ -172,25 +167,27 @@ struct RadonModel {
             const double al = fma(sa, a_c, mu_a), be = fma(sb, b_c, mu_b);
             double Ga0 = 0.0, Gb0 = 0.0, S20 = 0.0, Ga1 = 0.0, Gb1 = 0.0, S21 = 0.0;
             // SMALL: no unrolling inside the persistent NUTS kernel, whose hot code must stay inside the instruction cache
-            // (measured: 511 vs 562 ms per bench step); the stand-alone leapfrog/logp kernels unroll (540 vs 393 M evals/s)
-#pragma unroll(SMALL ? kRadonSmallUnroll : 4)
-            for (int b = 0, kb = 0; b < nblk; ++b, kb += 4) {
+            // (measured: 511 vs 562 ms per bench step; ping-ponging the prefetch registers with an unroll of 2: 526 vs 506);
+            // the stand-alone leapfrog/logp kernels unroll (540 vs 393 M evals/s).
+            // Padding slots hold (x, y) = (0, 0): their residual is -alpha exactly, so instead of masking every slot
+            // (2 selects + a compare per observation: a fifth of the loop's issue slots) the lane removes its padding's
+            // contribution after the row:  Ga += npad alpha,  S2 -= npad alpha^2,  Gb untouched (x = 0).
+#pragma unroll(SMALL ? 1 : 4)
+            for (int b = 0; b < nblk; ++b) {
                 ptr += 128;
                 const double2 n0 = ptr[0], n1 = ptr[32], n2 = ptr[64], n3 = ptr[96];
-                double r0 = c0.y - fma(be, c0.x, al), r1 = c1.y - fma(be, c1.x, al);
-                double r2 = c2.y - fma(be, c2.x, al), r3 = c3.y - fma(be, c3.x, al);
-                r0 = (kb < cnt) ? r0 : 0.0;  // padding of the row contributes exact zeros
-                r1 = (kb + 1 < cnt) ? r1 : 0.0;
-                r2 = (kb + 2 < cnt) ? r2 : 0.0;
-                r3 = (kb + 3 < cnt) ? r3 : 0.0;
+                const double r0 = c0.y - fma(be, c0.x, al), r1 = c1.y - fma(be, c1.x, al);
+                const double r2 = c2.y - fma(be, c2.x, al), r3 = c3.y - fma(be, c3.x, al);
                 S20 = fma(r0, r0, S20); Ga0 += r0; Gb0 = fma(r0, c0.x, Gb0);
                 S21 = fma(r1, r1, S21); Ga1 += r1; Gb1 = fma(r1, c1.x, Gb1);
                 S20 = fma(r2, r2, S20); Ga0 += r2; Gb0 = fma(r2, c2.x, Gb0);
                 S21 = fma(r3, r3, S21); Ga1 += r3; Gb1 = fma(r3, c3.x, Gb1);
                 c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }
-            const double Ga = Ga0 + Ga1, Gb = Gb0 + Gb1;
-            acc[0] += S20 + S21;
+            const double npad = (double)(4 * nblk - cnt);
+            const double Ga = fma(npad, al, Ga0 + Ga1), Gb = Gb0 + Gb1;
+            const double S2r = fma(-npad * al, al, S20 + S21);
+            acc[0] += live ? S2r : 0.0;  // an idle lane (no county in this row) saw only padding
             if (live) {  // county finished: its two gradient entries are complete
                 g_s[4 + c] = fma(sa_ie2, Ga, -a_c);
                 g_s[4 + J + c] = fma(sb_ie2, Gb, -b_c);

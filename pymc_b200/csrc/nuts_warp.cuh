@@ -31,14 +31,11 @@ namespace b200 {
 
 constexpr int kMaxLevels = 12;  // pending-subtree levels (max_treedepth <= 12)
 
-// UNTESTED CANDIDATE (off): carry a subtree's multinomial weight as the pair (m, s), log-weight = m + log(s), instead of
-// one log-weight.  A leaf is (-dE, 1); merging (m1, s1) and (m2, s2) gives m = max(m1, m2), s = s1 e^(m1-m) + s2 e^(m2-m):
-// one exp and no log per merge (the log costs ~75 instructions, 9 % of the kernel's stall samples), and no overflow for
-// any energy change because m carries the scale and 1 <= s <= number of leaves.  The pick probabilities are the same
-// numbers as logaddexp gives (nuts.py:465-467, :370-376) up to rounding.
-#ifndef B200_MS_WEIGHTS
-#define B200_MS_WEIGHTS 0
-#endif
+// A subtree's multinomial weight is carried as the pair (m, s), log-weight = m + log(s), instead of one log-weight.  A
+// leaf is (-dE, 1); merging (m1, s1) and (m2, s2) gives m = max(m1, m2), s = s1 e^(m1-m) + s2 e^(m2-m): one exp and no log
+// per merge, and no overflow for any energy change because m carries the scale and 1 <= s <= number of leaves.  The pick
+// probabilities are the numbers logaddexp gives (nuts.py:465-467, :370-376) up to rounding; measured on the bench
+// workload (round 2, profiles/r2_variants.md): 481.6 vs 506.3 ms per step, every golden tree decision unchanged.
 
 struct NutsDev {
     int C, n, tune, draws, max_td, early_td, adapt_step, mass_kind, momentum_source, store_warmup;
@@ -56,29 +53,52 @@ struct NutsDev {
     b200_chain_summary sm;
     double* scratch;            // per-chain global scratch
     long long scratch_stride;   // doubles per chain
+    // dynamic scheduling (see "Scheduling" below)
+    struct ChainCtx* ctx;       // [C] per-chain scalar state between segments
+    int* done;                  // [C] segments completed per chain
+    unsigned int* ticket;       // [1] next work unit
+    int seg_iters;              // iterations per work unit
 };
 
+// Scheduling.  A work unit is (chain, segment of `seg_iters` consecutive iterations).  Teams (a warp, or a CTA for W > 1)
+// of a PERSISTENT grid (every CTA resident) take units from a global ticket counter in segment-major order
+// (all chains' segment 0, then segment 1, ...) and keep the chain's state in global memory between segments (position,
+// inverse mass, adaptation scalars, stream position: ~3 KB per boundary).  A unit whose predecessor segment is still
+// running (only ever a LOWER ticket, held by a resident team: no deadlock) is waited for, so a slow chain runs back to
+// back while fast chains yield their slot.  Compared with "a CTA owns its chains for the whole run" this removes (i) the
+// idle warps of a CTA whose other chains are still running, (ii) the whole-wave quantisation of C chains over the resident
+// slots (2048 chains over 1184 warp slots cost 1.73 rounds instead of 2) and (iii) most of the straggler tail (per-chain
+// step sizes make the slowest chain 1.7x the mean).  A chain's arithmetic and stream consumption are unchanged, so
+// results stay bit-identical and independent of the schedule.
+struct ChainCtx {
+    double log_step, log_bar, hbar, fg_n, bg_n;
+    long long n_grad;
+    int da_count, k_samples, window, fg_m, fg_v, bg_m, bg_v, bad_at;
+};
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // global scratch layout per chain, in units of NP doubles
-enum { G_LQ = 0, G_LP, G_LG, G_RQ, G_RP, G_RG, G_PS, G_PQ, G_NEARP, G_FGM, G_FGV, G_BGM, G_BGV, G_STACK };
+enum { G_LQ = 0, G_LP, G_LG, G_RQ, G_RP, G_RG, G_PS, G_PQ, G_NEARP, G_FGM, G_FGV, G_BGM, G_BGV, G_Q, G_VAR, G_STACK };
 
 __host__ __device__ inline long long nuts_scratch_doubles(int NP, int levels) {
     return (long long)(G_STACK + 4 * levels) * NP;
 }
 // shared memory per warp (bytes): q, g, hot stack levels (level 0: 2 vectors, others: 4), scalars
-// UNTESTED CANDIDATE (off): cut the register live ranges across the model function -- the inverse mass `var` lives in
-// shared memory for the whole run and the momentum `p` is parked there around every evaluation, so the model function's
-// ~110 registers are not stacked on top of 2 x NPL persistent doubles (target: 168 registers without spills with
-// B200_SUBTREE_SMEM=1 -> 3 CTAs x 4 warps per SM).
-#ifndef B200_PARK_VECTORS
-#define B200_PARK_VECTORS 0
-#endif
 #ifndef B200_SUBTREE_SMEM
 #define B200_SUBTREE_SMEM 0  // 1: left.p / p_sum / proposal q of the subtree under construction live in shared memory
 #endif                       //    (frees 6*NPL registers per lane -> more resident warps); 0: in registers
 // (per chain; + 3 vectors when the subtree under construction is kept in shared memory; + the team's reduction pad)
 __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool subs = B200_SUBTREE_SMEM, int W = 1) {
-    const int vecs = 2 + (subs ? 3 : 0) + 2 * B200_PARK_VECTORS + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
-    return (size_t)vecs * NP * sizeof(double) + (4 + B200_MS_WEIGHTS) * kMaxLevels * sizeof(double) +
+    const int vecs = 2 + (subs ? 3 : 0) + (hot > 0 ? 2 + 4 * (hot - 1) : 0);
+    return (size_t)vecs * NP * sizeof(double) + 5 * kMaxLevels * sizeof(double) +
            (W > 1 ? W * 8 * sizeof(double) : 0);
 }
 
@@ -89,8 +109,8 @@ __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool sub
 #define B200_NUTS_MINBLOCKS 1  // __launch_bounds__ min CTAs/SM: the register budget knob
 #endif
 // W = warps per chain (team).  SUBS = subtree-under-construction vectors in shared memory instead of registers.
-#ifdef B200_NUTS_MAXREG  // untested candidate: an explicit register cap (e.g. 144 -> 14 warps/SM = all 2048 chains of the
-#define B200_NUTS_BOUNDS __maxnreg__(B200_NUTS_MAXREG)  // bench resident at once); cannot be combined with __launch_bounds__
+#ifdef B200_NUTS_MAXREG  // A/B knob: an explicit register cap for the chain-per-warp kernels (cannot be combined with bounds)
+#define B200_NUTS_BOUNDS __maxnreg__(W > 1 ? 255 : B200_NUTS_MAXREG)
 #else
 #define B200_NUTS_BOUNDS __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 : B200_NUTS_MINBLOCKS)
 #endif
@@ -114,24 +134,16 @@ __global__ void B200_NUTS_BOUNDS
 
     // `lane` is the thread's index inside its team (0 .. TS-1)
     const int lane = (W == 1) ? (threadIdx.x & 31) : (int)threadIdx.x;
-    const int wib = (W == 1) ? (threadIdx.x >> 5) : 0, wpb = (W == 1) ? (blockDim.x >> 5) : 1;
-    const int chain = blockIdx.x * wpb + wib;
-    if (chain >= P.C) return;  // no CTA-wide barrier after this point (W == 1); W > 1: the whole CTA leaves
+    const int wib = (W == 1) ? (threadIdx.x >> 5) : 0;
+    __shared__ unsigned int ticket_s;  // W > 1: the CTA's current ticket
 
     const int hot = P.hot_levels;
     double* ws = reinterpret_cast<double*>(smem_raw + data_bytes + wib * nuts_warp_smem_bytes(NP, hot, SUBS, W));
     double* q_s = ws;
     double* g_s = ws + NP;
     double* sub_s = ws + 2 * NP + lane;            // SUBS: left.p, p_sum, proposal q of the subtree under construction
-#if B200_PARK_VECTORS
-    double* var_s = ws + (SUBS ? 5 : 2) * NP + lane;   // inverse mass, resident in shared memory
-    double* park_s = var_s + NP;                       // momentum, parked around the model function
-    double* hot_base = ws + (SUBS ? 7 : 4) * NP;
-#define VAR(k) var_s[TS * (k)]
-#else
     double* hot_base = ws + (SUBS ? 5 : 2) * NP;
 #define VAR(k) var[k]
-#endif
     double lp_r[SUBS ? 1 : NPL], ps_r[SUBS ? 1 : NPL], pq_r[SUBS ? 1 : NPL];
     auto LPf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[TS * k]; else return lp_r[k]; };
     auto PSf = [&](int k) -> double& { if constexpr (SUBS) return sub_s[NP + TS * k]; else return ps_r[k]; };
@@ -143,12 +155,36 @@ __global__ void B200_NUTS_BOUNDS
     double* sc_pe = sc_logw + kMaxLevels;
     double* sc_plogp = sc_pe + kMaxLevels;
     double* sc_pidx = sc_plogp + kMaxLevels;
-#if B200_MS_WEIGHTS
     double* sc_s = sc_pidx + kMaxLevels;
     double* red = sc_s + kMaxLevels;     // W x 8 doubles, cross-warp reductions (W > 1)
-#else
-    double* red = sc_pidx + kMaxLevels;  // W x 8 doubles, cross-warp reductions (W > 1)
-#endif
+    const int n = P.n;
+    const int Ttot = P.tune + P.draws;
+    const int T_out = P.store_warmup ? Ttot : P.draws;
+    const int seg_iters = P.seg_iters > 0 ? P.seg_iters : Ttot;
+    const unsigned int n_seg = (unsigned int)((Ttot + seg_iters - 1) / seg_iters);
+    const unsigned int n_units = n_seg * (unsigned int)P.C;
+
+    // ---- work loop: one (chain, segment) unit per turn ---------------------------------------------------
+    for (;;) {
+    unsigned int unit;
+    if constexpr (W == 1) {
+        unit = 0;
+        if (lane == 0) unit = atomicAdd(P.ticket, 1u);
+        unit = __shfl_sync(B200_FULL_MASK, unit, 0);
+    } else {
+        __syncthreads();  // everyone is done with the previous unit (and with ticket_s)
+        if (threadIdx.x == 0) ticket_s = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        unit = ticket_s;
+    }
+    if (unit >= n_units) break;
+    const int seg = (int)(unit / (unsigned int)P.C);
+    const int chain = (int)(unit - (unsigned int)seg * (unsigned int)P.C);
+    const int it_begin = seg * seg_iters, it_end = min(Ttot, it_begin + seg_iters);
+    if (seg > 0) {  // the chain's previous segment may still be running on another team (every thread acquires)
+        while (ld_acquire_i32(P.done + chain) < seg) __nanosleep(64);
+        team_sync<W>();
+    }
     double* gs = P.scratch + (long long)chain * P.scratch_stride;
 
     // which: 0 = left.p, 1 = right.p, 2 = p_sum, 3 = proposal q.  Level 0 (a single leaf) keeps only 2, 3.
@@ -158,50 +194,58 @@ __global__ void B200_NUTS_BOUNDS
     };
     auto gvec = [&](int which) -> double* { return gs + (long long)which * NP; };
 
-    const int n = P.n;
-    const int Ttot = P.tune + P.draws;
-    const int T_out = P.store_warmup ? Ttot : P.draws;
-
-    // ---- per-chain persistent state ---------------------------------------------------------------
-#if B200_PARK_VECTORS
-    double p[NPL];
-#else
+    // ---- per-chain state: initialised by the first segment, carried through global memory afterwards ------------
     double var[NPL], p[NPL];
-#endif
+    int fg_m, fg_v, bg_m, bg_v, k_samples, window, da_count, bad_at;
+    double fg_n, bg_n, log_step, log_bar, hbar;
+    long long n_grad;
+    const double eps_init = P.eps0c ? P.eps0c[chain] : P.eps0;
+    const double da_mu = log(10.0 * eps_init);  // dual averaging (step_sizes.py:50-57)
+    if (seg == 0) {
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-        const int i = lane + TS * k;
-        q_s[i] = (i < n) ? P.q0[(long long)chain * n + i] : 0.0;
-        g_s[i] = 0.0;
-        VAR(k) = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
-        // Welford estimators: foreground starts at (mean0, var0 * weight, weight); background empty
-        if (P.mass_kind == B200_MASS_DIAG_ADAPT) {
-            gvec(G_FGM)[i] = (i < n && P.mean0) ? P.mean0[(long long)chain * n + i] : 0.0;
-            gvec(G_FGV)[i] = VAR(k) * P.init_weight;
-            gvec(G_BGM)[i] = 0.0;
-            gvec(G_BGV)[i] = 0.0;
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + TS * k;
+            q_s[i] = (i < n) ? P.q0[(long long)chain * n + i] : 0.0;
+            g_s[i] = 0.0;
+            VAR(k) = (i < n && P.var0) ? P.var0[(long long)chain * n + i] : 1.0;
+            // Welford estimators: foreground starts at (mean0, var0 * weight, weight); background empty
+            if (P.mass_kind == B200_MASS_DIAG_ADAPT) {
+                gvec(G_FGM)[i] = (i < n && P.mean0) ? P.mean0[(long long)chain * n + i] : 0.0;
+                gvec(G_FGV)[i] = VAR(k) * P.init_weight;
+                gvec(G_BGM)[i] = 0.0;
+                gvec(G_BGV)[i] = 0.0;
+            }
+        }
+        fg_m = G_FGM; fg_v = G_FGV; bg_m = G_BGM; bg_v = G_BGV;
+        fg_n = P.init_weight; bg_n = 0.0;
+        k_samples = 0; window = P.window;
+        log_step = log(eps_init); log_bar = log_step; hbar = 0.0;
+        da_count = 1;
+        n_grad = 0;
+        bad_at = -1;
+    } else {
+        const ChainCtx cx = P.ctx[chain];
+        fg_m = cx.fg_m; fg_v = cx.fg_v; bg_m = cx.bg_m; bg_v = cx.bg_v;
+        fg_n = cx.fg_n; bg_n = cx.bg_n; k_samples = cx.k_samples; window = cx.window;
+        log_step = cx.log_step; log_bar = cx.log_bar; hbar = cx.hbar; da_count = cx.da_count;
+        n_grad = cx.n_grad; bad_at = cx.bad_at;
+        const double* sq = gvec(G_Q); const double* sv = gvec(G_VAR);
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + TS * k;
+            q_s[i] = sq[i];
+            g_s[i] = 0.0;
+            VAR(k) = sv[i];
         }
     }
-    int fg_m = G_FGM, fg_v = G_FGV, bg_m = G_BGM, bg_v = G_BGV;
-    double fg_n = P.init_weight, bg_n = 0.0;
-    int k_samples = 0, window = P.window;
-
-    // dual averaging (step_sizes.py:50-57)
-    const double eps_init = P.eps0c ? P.eps0c[chain] : P.eps0;
-    double log_step = log(eps_init), log_bar = log_step, hbar = 0.0;
-    const double da_mu = log(10.0 * eps_init);
-    int da_count = 1;
-
     Pcg64 rng;
     {
         const b200_pcg64 r = P.rng[chain];
         rng.load(r.state_hi, r.state_lo, r.inc_hi, r.inc_lo);
     }
-    long long n_grad = 0;
-    int bad_at = -1;
     team_sync<W>();
 
-    for (int it = 0; it < Ttot; ++it) {
+    for (int it = it_begin; it < it_end && bad_at < 0; ++it) {
         const bool tuning = it < P.tune;
         const bool adapting = tuning && P.adapt_step;
 
@@ -218,17 +262,9 @@ __global__ void B200_NUTS_BOUNDS
             p[k] = (1.0 / sqrt(VAR(k))) * zz;
         }
         // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
-#if B200_PARK_VECTORS
-#pragma unroll
-        for (int k = 0; k < NPL; ++k) park_s[TS * k] = p[k];
-#endif
         team_sync<W>();
         const double logp0 = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
         team_sync<W>();
-#if B200_PARK_VECTORS
-#pragma unroll
-        for (int k = 0; k < NPL; ++k) p[k] = park_s[TS * k];
-#endif
         ++n_grad;
         double kin = 0.0;
 #pragma unroll
@@ -255,9 +291,7 @@ __global__ void B200_NUTS_BOUNDS
         }
         int L_idx = 0, R_idx = 0;
         double m_logw = 0.0, m_pe = E0, m_plogp = logp0;
-#if B200_MS_WEIGHTS
         double m_s = 1.0;
-#endif
         int m_pidx = 0;
         double accept_sum = 0.0, max_de = 0.0;  // sum of min(1, exp(-dE)): exp(log_accept_sum) of nuts.py:415 without the log
         int n_prop = 0, depth = 0;
@@ -284,9 +318,7 @@ __global__ void B200_NUTS_BOUNDS
             // ---- _build_subtree(edge, depth, +-eps): 2^depth leaves, merges driven by a binary counter --
             bool sub_div = false, sub_turn = false;
             double c_logw = 0.0, c_pe = 0.0, c_plogp = 0.0;
-#if B200_MS_WEIGHTS
             double c_s = 1.0;
-#endif
             int c_pidx = 0;
             const int n_leaf = 1 << depth;
             for (int leaf = 0; leaf < n_leaf; ++leaf) {
@@ -297,17 +329,9 @@ __global__ void B200_NUTS_BOUNDS
                     p[k] = fma(dt, g_s[i], p[k]);
                     q_s[i] = fma(es, VAR(k) * p[k], q_s[i]);
                 }
-#if B200_PARK_VECTORS
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) park_s[TS * k] = p[k];
-#endif
                 team_sync<W>();
                 const double logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
                 team_sync<W>();
-#if B200_PARK_VECTORS
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) p[k] = park_s[TS * k];
-#endif
                 ++n_grad;
                 double kk = 0.0;
 #pragma unroll
@@ -336,9 +360,7 @@ __global__ void B200_NUTS_BOUNDS
                     PQ(k) = q_s[lane + TS * k];
                 }
                 c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
-#if B200_MS_WEIGHTS
                 c_s = 1.0;
-#endif
 
                 // -- merge with pending left siblings while the counter carries (nuts.py:452-476)
                 int h = 0;
@@ -384,7 +406,6 @@ __global__ void B200_NUTS_BOUNDS
                     if (h) team_sum_n<W>(dots, lane, red);
                     const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
                                       (dots[4] <= 0) || (dots[5] <= 0);
-#if B200_MS_WEIGHTS
                     // weights (m, s): tree1 = (sc_logw[h], sc_s[h]), tree2 = (c_logw, c_s); P(pick tree2) = w2 / (w1 + w2)
                     const double t_m = sc_logw[h], t_s = sc_s[h];
                     const double dm = c_logw - t_m;
@@ -400,23 +421,6 @@ __global__ void B200_NUTS_BOUNDS
                     }
                     c_logw = fmax(c_logw, t_m);
                     c_s = ws;
-#else
-                    // logw = logaddexp(t, c) = max + log1p(e), e = exp(-|c - t|); the pick  log(u) < c - logw  is
-                    // u * (1 + e) < (c >= t ? 1 : e): same decision without evaluating log(u)
-                    const double t_logw = sc_logw[h];
-                    const double dlw = c_logw - t_logw;
-                    const double e_w = exp(-fabs(dlw));
-                    const double logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
-                                                     : (isnan(dlw) ? c_logw + t_logw : fmax(c_logw, t_logw) + log1p_abs(e_w));
-                    const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
-                    if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
-                        const double* t_pq = lvl(h, 3);
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + TS * k];
-                        c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
-                    }
-                    c_logw = logw;
-#endif
                     if (turn) {
                         sub_turn = true;
                         break;
@@ -448,9 +452,7 @@ __global__ void B200_NUTS_BOUNDS
                     }
                     if (lane == 0) {
                         sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
-#if B200_MS_WEIGHTS
                         sc_s[h] = c_s;
-#endif
                     }
                     team_sync<W>();
                 }
@@ -477,7 +479,6 @@ __global__ void B200_NUTS_BOUNDS
             }
             // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
             {
-#if B200_MS_WEIGHTS
                 // accept the new subtree's proposal iff u < w_new / w_old  (log(u) < log_size_new - log_size_old)
                 const double u = rng.next_double();
                 const double dm = c_logw - m_logw;
@@ -491,19 +492,6 @@ __global__ void B200_NUTS_BOUNDS
                 m_logw = fmax(c_logw, m_logw);
                 m_s = wo + wn;
             }
-#else
-                const double u = rng.next_double();
-                const double dlw = c_logw - m_logw;
-                const double e_w = exp(-fabs(dlw));
-                if (dlw >= 0.0 || u < e_w) {  // log(u) < c_logw - m_logw
-#pragma unroll
-                    for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = PQ(k);
-                    m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
-                }
-                m_logw = (dlw == 0.0) ? c_logw + 0.69314718055994530942
-                                      : (isnan(dlw) ? c_logw + m_logw : fmax(c_logw, m_logw) + log1p_abs(e_w));
-            }
-#endif
             // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
             {
                 const double* FARP = dir > 0 ? Lp : Rp;
@@ -621,7 +609,7 @@ __global__ void B200_NUTS_BOUNDS
 
     // ---- a frozen chain ("Bad initial energy"): the iterations that never ran are NaN in the output --------------
     if (bad_at >= 0) {
-        for (int t = bad_at; t < Ttot; ++t) {
+        for (int t = max(bad_at, it_begin); t < it_end; ++t) {
             if (!(P.store_warmup || t >= P.tune)) continue;
             const int t_out = P.store_warmup ? t : t - P.tune;
 #pragma unroll
@@ -632,23 +620,47 @@ __global__ void B200_NUTS_BOUNDS
             if (lane == 0) stats_sentinel(P.st, (long long)chain * T_out + t_out);
         }
     }
-    // ---- end of run: hand the streams and adaptation results back --------------------------------------
+    // ---- end of the segment: the stream position goes back to the caller's array (it is also where the next segment
+    //      picks it up); last segment: adaptation results; otherwise: the chain's state for the next segment ------------
+    const bool last_seg = it_end >= Ttot;
     if (lane == 0) {
         b200_pcg64 r;
         r.state_hi = (uint64_t)(rng.state >> 64); r.state_lo = (uint64_t)rng.state;
         r.inc_hi = (uint64_t)(rng.inc >> 64); r.inc_lo = (uint64_t)rng.inc;
         P.rng[chain] = r;
-        if (P.sm.grad_evals) P.sm.grad_evals[chain] = n_grad;
-        if (P.sm.bad_energy_at) P.sm.bad_energy_at[chain] = bad_at;
-        if (P.sm.final_step_size) P.sm.final_step_size[chain] = exp(log_bar);
+        if (last_seg) {
+            if (P.sm.grad_evals) P.sm.grad_evals[chain] = n_grad;
+            if (P.sm.bad_energy_at) P.sm.bad_energy_at[chain] = bad_at;
+            if (P.sm.final_step_size) P.sm.final_step_size[chain] = exp(log_bar);
+        } else {
+            ChainCtx cx;
+            cx.log_step = log_step; cx.log_bar = log_bar; cx.hbar = hbar; cx.fg_n = fg_n; cx.bg_n = bg_n;
+            cx.n_grad = n_grad; cx.da_count = da_count; cx.k_samples = k_samples; cx.window = window;
+            cx.fg_m = fg_m; cx.fg_v = fg_v; cx.bg_m = bg_m; cx.bg_v = bg_v; cx.bad_at = bad_at;
+            P.ctx[chain] = cx;
+        }
     }
-    if (P.sm.final_var) {
+    if (last_seg) {
+        if (P.sm.final_var) {
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                if (i < n) P.sm.final_var[(long long)chain * n + i] = VAR(k);
+            }
+        }
+    } else {
+        double* sq = gvec(G_Q); double* sv = gvec(G_VAR);
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + TS * k;
-            if (i < n) P.sm.final_var[(long long)chain * n + i] = VAR(k);
+            sq[i] = q_s[i];
+            sv[i] = VAR(k);
         }
+        __threadfence();   // every thread's state writes are visible device-wide before the segment is published
+        team_sync<W>();
+        if (lane == 0) st_release_i32(P.done + chain, seg + 1);
     }
+    }  // work loop
 }
 
 #undef VAR

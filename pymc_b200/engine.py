@@ -21,10 +21,29 @@ def _f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-class CompiledModel:
-    """Observed data resident in HBM + dispatch to the model's fused logp/grad device function."""
+def _ir_spec(ir) -> ModelSpec:
+    """The ModelSpec face (layout, transforms, initial point) of a model that runs on the generic IR device function."""
+    from . import models
 
-    def __init__(self, spec: ModelSpec, device: int | None = None):
+    vars_, n = models._layout([(v.name, v.rv_name, v.size, v.transform, v.bounds) for v in ir.vars])
+    return ModelSpec(models.KIND_IR, n, vars_, data={}, meta={"initial_point": ir.initial_point(), "ir": ir})
+
+
+class CompiledModel:
+    """Observed data resident in HBM + dispatch to the model's fused logp/grad device function.
+
+    ``spec`` is either a ``pymc_b200.ir.ModelIR`` (the general interface: any model of the closed factor set; routed to
+    a hand-specialised kernel when ``ir.specialise`` recognises its shape, otherwise evaluated by the generic IR device
+    function) or a ``models.ModelSpec`` naming one of the hand-written kernels directly (the GEMM-shaped configs)."""
+
+    def __init__(self, spec, device: int | None = None, specialise: bool = True):
+        from . import ir as _ir
+
+        self.ir = None
+        if isinstance(spec, _ir.ModelIR):
+            self.ir = spec
+            fast = _ir.specialise(spec) if specialise else None
+            spec = fast if fast is not None else _ir_spec(spec)
         self.spec = spec
         self.n = spec.n
         self._lib = _lib.load()
@@ -62,6 +81,10 @@ class CompiledModel:
             d.x, d.aux = hold(data["prec"], np.float64), hold(data["cov"], np.float64)
             d.m1, d.m2 = hold(Linv.T, np.float64), hold(L, np.float64)
             d.scalar0 = spec.meta["logdet_L"]
+        elif spec.name == "ir":
+            c_ir, keep_ir = _lib.build_ir(_ir.lower(self.ir))
+            keep += keep_ir + [c_ir]
+            d.ir = C.addressof(c_ir)
         handle = C.c_void_p()
         _lib.check(self._lib.b200_model_create(C.byref(d), C.byref(handle)))
         self._h = handle

@@ -24,6 +24,7 @@ KIND_RADON = 2
 KIND_LOGISTIC = 3
 KIND_STOCHVOL = 4
 KIND_MVGAUSS = 5
+KIND_IR = 6  # any ModelIR on the generic device function (pymc_b200.ir)
 
 KIND_NAMES = {
     KIND_STD_NORMAL: "std_normal",
@@ -32,6 +33,7 @@ KIND_NAMES = {
     KIND_LOGISTIC: "logistic",
     KIND_STOCHVOL: "stochvol",
     KIND_MVGAUSS: "mvgauss",
+    KIND_IR: "ir",
 }
 
 

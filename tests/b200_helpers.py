@@ -20,6 +20,8 @@ SPEC_OF = {
     "mvgauss_dense_stepadapt": lambda: models.mvgauss(n=60, seed=5),
     "logistic_small_adapt": lambda: models.logistic(n_rows=400, n_features=8, seed=3),
     "logistic_small_fixed": lambda: models.logistic(n_rows=400, n_features=8, seed=3),
+    "logistic_k128_fixed": lambda: models.logistic(n_rows=8192, n_features=128, seed=3),
+    "mvgauss_n10000_fixed": models.mvgauss,
 }
 TREE_KW = {"radon_small_adapt": dict(max_treedepth=6, early_max_treedepth=4)}
 DISCRETE = ["depth", "tree_size", "index_in_trajectory", "diverging", "reached_max_treedepth"]
@@ -58,6 +60,8 @@ def gpu_free_run(cm, d, name, draws=None):
             t, dr = (T, 0) if draws is not None else (tune, int(d["draws"]))
         else:
             t, dr = 0, T
+            if not np.isnan(d["eps"][0]):
+                kw["eps0"] = d["eps"]
     elif bool(d["adapt"]):
         kw.update(mass="diag_adapt", mean0=d["q0"], var0=d["init_var"], adapt_step_size=True, step_scale=float(d["step_scale"]))
         t, dr = (T, 0) if draws is not None else (tune, int(d["draws"]))

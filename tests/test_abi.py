@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200nuts.h but not exported"
     assert {s[0] for s in _lib.SYMBOLS} == set(names), "ctypes table and header disagree"
-    assert lib.b200_version() == 100
+    assert lib.b200_version() == 200
 
 
 def test_struct_layouts_match_header():

@@ -25,7 +25,7 @@ def _gen_from_state(state_u64x4):
 
 @pytest.mark.parametrize("name", ["std_normal_fixed", "eight_schools_fixed", "radon_fixed", "std_normal_team_fixed",
                                   "stochvol_small_fixed", "stochvol_fixed", "logistic_small_fixed",
-                                  "mvgauss_dense_fixed"])
+                                  "mvgauss_dense_fixed", "logistic_k128_fixed"])
 def test_fixed_step_chains_reproduce_golden(golden, name):
     d = golden(name)
     spec = SPEC_OF[name]()

@@ -130,6 +130,15 @@ typedef struct b200_ir {
 #define B200_MASS_DIAG 0       /* QuadPotentialDiag      :582-630  (fixed diagonal)                   */
 #define B200_MASS_DIAG_ADAPT 1 /* QuadPotentialDiagAdapt :211-355  (per-chain Welford windows)        */
 #define B200_MASS_DENSE 2      /* QuadPotentialFull      :680-725  (fixed dense covariance)           */
+#define B200_MASS_DIAG_ADAPT_GRAD 3 /* QuadPotentialDiagAdaptExp :493-579 with use_grads (init="jitter+adapt_diag_grad",
+                                     * pymc/sampling/mcmc.py:1895-1912): var = sqrt(ewvar(draws) / ewvar(gradients));
+                                     * persistent engine only */
+
+/* step methods sharing BaseHMC.astep (hmc/base_hmc.py:196-288) */
+#define B200_SAMPLER_NUTS 0 /* NUTS._hamiltonian_step          hmc/nuts.py:204-225 */
+#define B200_SAMPLER_HMC 1  /* HamiltonianMC._hamiltonian_step hmc/hmc.py:143-200 (+ the uniform(0.85, 1.15) step-size jitter
+                             * of hmc.py:35-36, drawn from the chain's step stream); persistent engine only.  Stats: tree_size =
+                             * n_steps, mean_tree_accept = accept, index_in_trajectory = n_steps if accepted else 0, depth = 0 */
 
 /* where the momentum noise z ~ N(0,I) of `potential.random()` (quadpotential.py:323-326) comes from */
 #define B200_MOMENTUM_DEVICE_PHILOX 0 /* generated on device: Philox4x32-10 + Box-Muller, keyed per chain   */
@@ -163,6 +172,30 @@ typedef struct b200_pcg64 {
     uint64_t inc_hi, inc_lo;
 } b200_pcg64;
 
+/* Per-chain sampler state between calls: what BaseHMC.sampling_state carries for a NUTS/HMC chain with a diagonal adaptive
+ * potential (hmc/base_hmc.py:61-71: iter_count, step_adapt, potential; step_sizes.py:26-38 StepSizeState;
+ * quadpotential.py:189-208 QuadPotentialDiagAdaptState with its two WeightedVarianceState, :396-403).  Arrays of length C
+ * ([C][n] where noted) in the memory space of the call.  Used (i) to checkpoint / resume chains, (ii) to run warm-up in
+ * windows with the estimators pooled over chains and GPUs in between (pymc_b200.parallel.pooled_warmup).
+ * For DIAG_ADAPT_GRAD the four estimator arrays hold (mean, var) of the draws (fg_*) and of the gradients (bg_*). */
+typedef struct b200_chain_state {
+    double* q;          /* [C][n] current position                                              */
+    double* log_step;   /* DualAverageAdaptation._log_step                                        */
+    double* log_bar;    /*                       ._log_bar                                         */
+    double* hbar;       /*                       ._hbar                                            */
+    int32_t* da_count;  /*                       ._count                                           */
+    int32_t* n_samples; /* QuadPotentialDiagAdapt._n_samples                                      */
+    int32_t* window;    /*                       .adaptation_window                               */
+    double* var;        /* [C][n]                ._var                                             */
+    double* fg_n;       /* foreground estimator: n_samples, mean [C][n], raw_var [C][n]            */
+    double* fg_mean;
+    double* fg_m2;
+    double* bg_n;       /* background estimator                                                    */
+    double* bg_mean;
+    double* bg_m2;
+    int64_t* n_grad;    /* logp+grad evaluations so far                                            */
+} b200_chain_state;
+
 /* Sampler configuration: the keyword surface of pm.NUTS / BaseHMC (hmc/nuts.py:132, hmc/base_hmc.py:82-98). */
 typedef struct b200_nuts_cfg {
     int32_t chains;              /* C: independent chains in this call                                */
@@ -186,6 +219,19 @@ typedef struct b200_nuts_cfg {
     int32_t adaptation_window;   /* default 101                                                       */
     int32_t discard_window;      /* default 50                                                        */
     uint64_t philox_seed;        /* key for B200_MOMENTUM_DEVICE_PHILOX                               */
+    int32_t sampler;             /* B200_SAMPLER_*; default NUTS                                      */
+    int32_t max_steps;           /* HMC: default 1024                                                 */
+    double path_length;          /* HMC: default 2.0                                                  */
+    double mass_alpha;           /* DIAG_ADAPT_GRAD: decay rate, default 0.02                         */
+    int32_t stop_adaptation;     /* DIAG_ADAPT_GRAD: stop after this many updates; < 0 = never (init_nuts: tune - 50 if tune > 250) */
+    int32_t iter_begin;          /* this call runs iterations [iter_begin, iter_begin + iter_count) of the tune + draws schedule */
+    int32_t iter_count;          /* 0 = all remaining (tune + draws - iter_begin); outputs / z hold exactly these iterations   */
+    const b200_chain_state* resume;  /* NULL: chains start fresh (iter_begin must be 0); else the state exported by the previous call */
+    b200_chain_state* save;          /* NULL or where to export the state after the last iteration of this call                */
+    int32_t constrain_draws;     /* 1: draws_out holds the CONSTRAINED values (backward transforms of b200_model_set_transforms
+                                  * applied where a draw is recorded: the per-draw post-processing of backends/ndarray.py:108
+                                  * fused into the kernel); 0: unconstrained positions */
+    int32_t reserved;
 } b200_nuts_cfg;
 
 /* Per-draw sampler statistics, struct-of-arrays [C][T] with T = store_warmup ? tune+draws : draws.
@@ -218,7 +264,8 @@ int b200_version(void);
 const char* b200_last_error(void);
 /* sizeof() of the ABI structs as this library was compiled, so a host binding can verify its mirrors before passing
  * pointers: which = 0 b200_model_desc, 1 b200_nuts_cfg, 2 b200_stats, 3 b200_chain_summary, 4 b200_pcg64, 5 b200_ir,
- * 6 b200_ir_var, 7 b200_ir_prior, 8 b200_ir_term, 9 b200_ir_lik, 10 b200_ir_ar1, 11 b200_ir_param, 12 b200_ir_factor;
+ * 6 b200_ir_var, 7 b200_ir_prior, 8 b200_ir_term, 9 b200_ir_lik, 10 b200_ir_ar1, 11 b200_ir_param, 12 b200_ir_factor,
+ * 13 b200_chain_state;
  * -1 for an unknown index. */
 int b200_struct_size(int which);
 
@@ -230,7 +277,21 @@ int b200_set_device(int device);
 /* Replaces: Model.logp_dlogp_function(ravel_inputs=True) -> ValueGradFunction
  *           (pymc/model/core.py:464-529, :142-305) -- the compile step. */
 int b200_model_create(const b200_model_desc* desc, b200_model** out);
+/* Arithmetic of the dense contractions of a GEMM-shaped model (affects b200_logp_dlogp and b200_nuts_run of that handle).
+ *   B200_PRECISION_FP64      IEEE fp64 on the fp64 tensor path (DMMA) -- the parity mode, default.
+ *   B200_PRECISION_TC_FP16X2 LOGISTIC only: X.beta and X^T r on the 5th-generation tensor cores (tcgen05, TMEM, TMA) with
+ *                            every fp64 operand split into two fp16 pieces and fp32 accumulation, drained into fp64 every
+ *                            2048 rows; gradient ~1e-7 relative (measured: profiles/), ~10x the DMMA throughput.
+ * The reference computes in floatX = float64 (pymc/pytensorf.py); this is the "tensor cores where the logp really is a
+ * dense matvec" performance mode of north_star, with its error stated next to the number. */
+#define B200_PRECISION_FP64 0
+#define B200_PRECISION_TC_FP16X2 1
+int b200_model_set_precision(b200_model* model, int32_t mode);
 void b200_model_destroy(b200_model* model);
+/* Per-element backward transforms of the value variables (kind[n]: 0 identity, 1 exp, 2 lo + (hi - lo) sigmoid), used when
+ * b200_nuts_cfg.constrain_draws is set.  Replaces the compiled "unobserved values" function the reference evaluates per
+ * draw (pymc/backends/base.py:184-191, ndarray.py:108; transforms pymc/logprob/transforms.py:880-891, :1026-1045). */
+int b200_model_set_transforms(b200_model* model, const int8_t* kind, const double* lo, const double* hi);
 int b200_model_n(const b200_model* model);
 
 /* Replaces: ValueGradFunction._pytensor_function(q) -> (logp, dlogp), batched over C points

@@ -196,9 +196,75 @@ def fullsize_cases():
     np.savez_compressed(os.path.join(OUT, "mvgauss_n10000_fixed.npz"), **d)
 
 
+def run_reference_generic(spec, q0, *, seed, tune, draws, step_kind="nuts", potential, adapt=True, step_kwargs=None):
+    """One chain through the verbatim reference with a caller-built potential and step class (NUTS | HamiltonianMC)."""
+    f = logp_numpy.make_logp(spec)
+    start = {v.name: q0[v.offset : v.offset + v.size].copy() for v in spec.vars}
+    make = ref_loader.make_hmc if step_kind == "hmc" else ref_loader.make_nuts
+    step, _ = make(f, spec.var_sizes, start, potential=potential, step_rng=0, adapt_step_size=adapt, **(step_kwargs or {}))
+    step.setup_chain(np.random.default_rng(seed), tune, draws)
+    if tune == 0:
+        step.tune = False
+    pt, qs, sts, pre_rng = start, [], [], []
+    for i in range(tune + draws):
+        if i == tune:
+            step.stop_tuning()
+        s = step.rng.bit_generator.state["state"]
+        pre_rng.append([s["state"] >> 64, s["state"] & (2**64 - 1), s["inc"] >> 64, s["inc"] & (2**64 - 1)])
+        pt, st = step.step(pt)
+        qs.append(np.concatenate([np.ravel(pt[v.name]) for v in spec.vars]))
+        sts.append(st[0])
+    return np.array(qs), sts, np.array(pre_rng, dtype=np.uint64), step
+
+
+def f3_cases():
+    """HamiltonianMC (hmc/hmc.py) and init="jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp) goldens."""
+    qp = ref_loader.quadpotential()
+    rng = np.random.default_rng(51)
+    for name, spec_name, args in [("eight_schools", "eight_schools", {}), ("radon", "radon", {})]:
+        spec = models.BUILDERS[spec_name](**args)
+        n = spec.n
+        C = 2
+        q0s = [spec.initial_point() + rng.uniform(-1, 1, n) for _ in range(C)]
+        seeds = [901 + c for c in range(C)]
+        # -- HMC, adaptive (dual averaging at target 0.65 + DiagAdapt), cold start
+        tune, draws = 40, 10
+        Q, ST, PR = [], [], []
+        for c in range(C):
+            pot = qp.QuadPotentialDiagAdapt(n, q0s[c].copy(), np.ones(n), 10)
+            q, sts, pre, step = run_reference_generic(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, step_kind="hmc",
+                                                      potential=pot)
+            Q.append(q); ST.append(sts); PR.append(pre)
+        out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, draws_q=np.array(Q), pre_rng=np.array(PR),
+                   z=np.array([noise(s, tune + draws, n) for s in seeds]))
+        for k, kk in [("n_steps", "tree_size"), ("accept", "mean_tree_accept"), ("energy", "energy"), ("energy_error", "energy_error"),
+                      ("model_logp", "model_logp"), ("step_size", "step_size"), ("step_size_bar", "step_size_bar"),
+                      ("diverging", "diverging"), ("accepted", "accepted")]:
+            out["stat_" + kk] = np.array([[s[k] for s in sts] for sts in ST])
+        np.savez_compressed(os.path.join(OUT, name + "_hmc_adapt.npz"), **out)
+        print(name + "_hmc_adapt", "leapfrogs", int(out["stat_tree_size"].sum()), "accepted", float(out["stat_accepted"].mean()))
+        # -- NUTS + DiagAdaptExp(use_grads), short discard window so the gradient-based updates start at draw 21
+        tune, draws = 60, 10
+        Q, ST, PR, FV = [], [], [], []
+        for c in range(C):
+            pot = qp.QuadPotentialDiagAdaptExp(n, q0s[c].copy(), alpha=0.02, use_grads=True, stop_adaptation=50, discard_window=10)
+            q, sts, pre, step = run_reference_generic(spec, q0s[c], seed=seeds[c] + 50, tune=tune, draws=draws, potential=pot)
+            Q.append(q); ST.append(sts); PR.append(pre); FV.append(np.array(step.potential._var))
+        out = dict(q0=np.array(q0s), seeds=np.array(seeds) + 50, tune=tune, draws=draws, draws_q=np.array(Q), pre_rng=np.array(PR),
+                   z=np.array([noise(s + 50, tune + draws, n) for s in seeds]), final_var=np.array(FV), alpha=0.02,
+                   stop_adaptation=50, discard_window=10)
+        for k in STAT_KEYS:
+            out["stat_" + k] = np.array([[s[k] for s in sts] for sts in ST])
+        np.savez_compressed(os.path.join(OUT, name + "_adapt_grad.npz"), **out)
+        print(name + "_adapt_grad", "grad evals", int(out["stat_tree_size"].sum()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lockstep":
         lockstep_cases()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "f3":
+        f3_cases()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize":
         fullsize_cases()

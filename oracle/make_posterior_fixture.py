@@ -50,9 +50,14 @@ def main():
     ess = diagnostics.ess_bulk(x)
     rhat = diagnostics.rhat(x) if hasattr(diagnostics, "rhat") else np.zeros(x.shape[-1])
     mean, sd = x.mean((0, 1)), x.std((0, 1))
+    # Monte Carlo error of the VARIANCE estimate: (x - mean)^2 is itself a chain, with its own (smaller) effective sample
+    # size -- the funnel directions (log sigma_b) have heavy-tailed squared deviations
+    dev2 = (x - mean) ** 2
+    ess_var = diagnostics.ess_bulk(dev2)
+    var_mcse = dev2.std((0, 1)) / np.sqrt(ess_var)
     path = os.path.join(ROOT, "tests", "golden", "radon_posterior_oracle.npz")
     np.savez_compressed(path, mean=mean, sd=sd, ess=ess, mcse_mean=sd / np.sqrt(ess), mcse_sd=sd / np.sqrt(2 * ess),
-                        chains=CHAINS, tune=TUNE, draws=DRAWS, seed=SEED, divergences=sum(o[1] for o in out), rhat=rhat)
+                        var=sd**2, ess_var=ess_var, var_mcse=var_mcse, chains=CHAINS, tune=TUNE, draws=DRAWS, seed=SEED, divergences=sum(o[1] for o in out), rhat=rhat)
     print(f"radon posterior fixture: {CHAINS} x ({TUNE}+{DRAWS}), min ESS {ess.min():.0f}, max rhat {np.max(rhat):.4f}, "
           f"divergences {sum(o[1] for o in out)} -> {path}")
 

@@ -14,6 +14,8 @@ It restates, function by function, what the reference does for one NUTS transiti
   * ``DiagMass``             <- QuadPotentialDiag / QuadPotentialDiagAdapt + _WeightedVariance
                                 hmc/quadpotential.py:582-630, :211-355, :405-448
   * ``DenseMass``            <- QuadPotentialFull        quadpotential.py:680-725
+  * ``DiagMassExp``          <- QuadPotentialDiagAdaptExp + _ExpWeightedVariance   quadpotential.py:458-579
+  * ``Oracle.hmc_draw``      <- HamiltonianMC._hamiltonian_step + unif step jitter   hmc/hmc.py:35-36, :143-200
 
 It performs the same floating-point operations with the same NumPy/BLAS calls in the same order
 and consumes the two per-chain PCG64 streams in the same order, so that on
@@ -104,6 +106,40 @@ class DiagMass:
             self.bg = _Welford(self.n)
             self.window = int(self.window * self.mult)
         self.k += 1
+
+
+class DiagMassExp(DiagMass):
+    """QuadPotentialDiagAdaptExp (quadpotential.py:493-579) with use_grads=True: exponentially weighted variances of the
+    draws and of their gradients (_ExpWeightedVariance :458-483); var = sqrt(var_draws / var_grads) after 2 * discard
+    draws; what init="jitter+adapt_diag_grad" builds (pymc/sampling/mcmc.py:1895-1912: alpha=0.02, stop = tune - 50)."""
+
+    def __init__(self, n, *, alpha=0.02, stop_adaptation=None, discard_window=50, initial_mean=None):
+        self.alpha, self.stop = float(alpha), (np.inf if stop_adaptation is None else stop_adaptation)
+        super().__init__(np.ones(n), adapt=True, initial_mean=initial_mean, initial_weight=0.0, discard_window=discard_window)
+
+    def reset(self):
+        super().reset()
+        self.est = self.est_g = None
+
+    def _add(self, e, value):
+        mean, var = e
+        delta = value - mean
+        mean[...] += self.alpha * delta
+        var[...] = (1 - self.alpha) * (var + self.alpha * delta**2)
+
+    def update(self, q, grad, tune):
+        if tune and self.k < self.stop:
+            if self.k > self.discard:
+                self._add(self.est, q)
+                self._add(self.est_g, grad)
+            elif self.k == self.discard:
+                self.est = [q.copy(), np.zeros_like(q)]
+                self.est_g = [grad.copy(), np.zeros_like(grad)]
+            if self.k > 2 * self.discard:
+                self.var = np.sqrt(self.est[1] / self.est_g[1])
+                self.std = np.sqrt(self.var)
+                self.inv_std = 1.0 / self.std
+            self.k += 1
 
 
 class DenseMass:
@@ -290,7 +326,9 @@ class Oracle:
     reference's (base_hmc.py:82-98, nuts.py:132)."""
 
     def __init__(self, logp_dlogp, mass, *, step_scale=0.25, adapt_step_size=True, target_accept=0.8,
-                 gamma=0.05, k=0.75, t0=10, Emax=1000.0, max_treedepth=10, early_max_treedepth=8):
+                 gamma=0.05, k=0.75, t0=10, Emax=1000.0, max_treedepth=10, early_max_treedepth=8, sampler="nuts",
+                 path_length=2.0, max_steps=1024):
+        self.sampler, self.path_length, self.max_steps = sampler, path_length, max_steps
         self.f = logp_dlogp
         self.mass = mass
         self.n = mass.n
@@ -349,8 +387,58 @@ class Oracle:
             hit_max = not self.tune
         return tr, div, hit_max
 
+    # hmc.py:143-200 (HamiltonianMC._hamiltonian_step); the step size is jittered by unif() (hmc.py:35-36) in astep
+    def _hmc_transition(self, start, eps):
+        n_steps = max(1, int(self.path_length / eps))
+        n_steps = min(self.max_steps, n_steps)
+        state = start
+        for _ in range(n_steps):
+            state = self._leapfrog(eps, state)
+        div = False
+        if not np.isfinite(state.energy):
+            div = True
+        de = state.energy - start.energy
+        if np.isnan(de):
+            de = np.inf
+        if np.abs(de) > self.Emax:
+            div = True
+        accept = min(1, np.exp(-de))
+        if div or self.rng.random() >= accept:
+            end, accepted = start, False
+        else:
+            end, accepted = state, True
+        return end, state, n_steps, accept, de, div, accepted
+
+    def hmc_draw(self, q0, z=None):
+        """One HamiltonianMC transition (BaseHMC.astep with step_rand = unif, hmc.py:141)."""
+        q0 = np.asarray(q0, dtype="float64")
+        if z is None:
+            z = self.mass.rng.normal(size=self.n)
+        p0 = self.mass.momentum(z)
+        start = self._start_state(q0, p0)
+        if not np.isfinite(start.energy):
+            raise BadInitialEnergy(f"Bad initial energy at iteration {self.iter_count}")
+        adapting = self.tune and self.adapt_step_size
+        eps = self.da.current(adapting)
+        eps_j = self.rng.uniform(0.85, 1.15) * eps
+        end, last, n_steps, accept, de, div, accepted = self._hmc_transition(start, eps_j)
+        self.da.update(accept, adapting)
+        self.mass.update(end.q, end.grad, self.tune)
+        if not self.tune:
+            self.divergences += bool(div)
+        self.iter_count += 1
+        stats = {
+            "depth": 0, "step_size": float(np.exp(self.da.log_step)), "step_size_bar": float(np.exp(self.da.log_bar)),
+            "mean_tree_accept": float(accept), "tree_size": n_steps, "diverging": bool(div), "divergences": self.divergences,
+            "energy_error": de, "energy": last.energy, "max_energy_error": de, "model_logp": last.logp,
+            "index_in_trajectory": n_steps if accepted else 0, "reached_max_treedepth": False, "tune": self.tune,
+        }
+        return end.q, stats
+
     # base_hmc.py:196-288
     def draw(self, q0, z=None):
+        if self.sampler == "hmc":
+            return self.hmc_draw(q0, z)
         """One transition from q0.  ``z``: optional pre-drawn N(0,1)^n momentum noise (otherwise drawn
         from the potential stream exactly like ``potential.random()``)."""
         q0 = np.asarray(q0, dtype="float64")

@@ -200,5 +200,16 @@ def make_nuts(logp_dlogp, var_sizes, start_point, *, potential=None, step_rng=0,
     return step, model
 
 
+def make_hmc(logp_dlogp, var_sizes, start_point, *, potential=None, step_rng=0, **hmc_kwargs):
+    """Build the reference ``HamiltonianMC`` step method (hmc/hmc.py) around a NumPy ``q -> (logp, grad)`` callable."""
+    mods = load()
+    HMC = mods["pymc.step_methods.hmc.hmc"].HamiltonianMC
+    model = FakeModel(var_sizes, start_point)
+    func = LogpDlogp(logp_dlogp)
+    step = HMC(vars=model.value_vars, model=model, potential=potential, logp_dlogp_func=func,
+               initial_point=model.initial_point(), rng=step_rng, **hmc_kwargs)
+    return step, model
+
+
 def quadpotential():
     return load()["pymc.step_methods.hmc.quadpotential"]

@@ -14,8 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "libb200nuts.so"))  # override: A/B builds while tuning
 
 MEM_HOST, MEM_DEVICE = 0, 1
-MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE = 0, 1, 2
+MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE, MASS_DIAG_ADAPT_GRAD = 0, 1, 2, 3
+SAMPLER_NUTS, SAMPLER_HMC = 0, 1
 MOMENTUM_DEVICE_PHILOX, MOMENTUM_HOST_BUFFER = 0, 1
+PRECISION_FP64, PRECISION_TC_FP16X2 = 0, 1
 
 
 class B200Error(RuntimeError):
@@ -134,6 +136,18 @@ class Pcg64State(C.Structure):
 PCG64_DTYPE = np.dtype([("state_hi", "<u8"), ("state_lo", "<u8"), ("inc_hi", "<u8"), ("inc_lo", "<u8")])
 
 
+STATE_FIELDS = [  # b200_chain_state: (name, dtype, per-chain vector?)
+    ("q", np.float64, True), ("log_step", np.float64, False), ("log_bar", np.float64, False), ("hbar", np.float64, False),
+    ("da_count", np.int32, False), ("n_samples", np.int32, False), ("window", np.int32, False), ("var", np.float64, True),
+    ("fg_n", np.float64, False), ("fg_mean", np.float64, True), ("fg_m2", np.float64, True), ("bg_n", np.float64, False),
+    ("bg_mean", np.float64, True), ("bg_m2", np.float64, True), ("n_grad", np.int64, False),
+]
+
+
+class ChainStateC(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _, _ in STATE_FIELDS]
+
+
 class NutsCfg(C.Structure):
     _fields_ = [
         ("chains", C.c_int32),
@@ -156,6 +170,17 @@ class NutsCfg(C.Structure):
         ("adaptation_window", C.c_int32),
         ("discard_window", C.c_int32),
         ("philox_seed", C.c_uint64),
+        ("sampler", C.c_int32),
+        ("max_steps", C.c_int32),
+        ("path_length", C.c_double),
+        ("mass_alpha", C.c_double),
+        ("stop_adaptation", C.c_int32),
+        ("iter_begin", C.c_int32),
+        ("iter_count", C.c_int32),
+        ("resume", C.c_void_p),
+        ("save", C.c_void_p),
+        ("constrain_draws", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -201,6 +226,8 @@ SYMBOLS = [
     ("b200_model_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
     ("b200_model_destroy", None, [C.c_void_p]),
     ("b200_model_n", C.c_int, [C.c_void_p]),
+    ("b200_model_set_precision", C.c_int, [C.c_void_p, C.c_int32]),
+    ("b200_model_set_transforms", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_logp_dlogp", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     (
         "b200_leapfrog",
@@ -228,12 +255,13 @@ def load() -> C.CDLL:
             raise B200Error(f"{LIB_PATH} is missing: build the CUDA engine first (./build.sh); there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)
         for name, restype, argtypes in SYMBOLS:
-            if name == "b200_struct_size" and not hasattr(lib, name):
+            if name in ("b200_struct_size", "b200_model_set_precision", "b200_model_set_transforms") and not hasattr(lib, name):
                 continue  # an A/B build (B200_LIB=...) older than ABI 0.2.0; tests/test_abi.py requires it of the in-tree library
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        mirrors = [ModelDesc, NutsCfg, Stats, ChainSummary, Pcg64State, Ir, IrVar, IrPrior, IrTerm, IrLik, IrAr1, IrParam, IrFactor]
+        mirrors = [ModelDesc, NutsCfg, Stats, ChainSummary, Pcg64State, Ir, IrVar, IrPrior, IrTerm, IrLik, IrAr1, IrParam, IrFactor,
+                   ChainStateC]
         for which, cls in enumerate(mirrors if hasattr(lib, "b200_struct_size") else []):
             if lib.b200_struct_size(which) != C.sizeof(cls):
                 raise B200Error(f"ABI mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, {lib.b200_struct_size(which)} in "

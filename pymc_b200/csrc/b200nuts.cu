@@ -15,6 +15,7 @@
 
 #include "dense.cuh"
 #include "ir_model.cuh"
+#include "logistic_tc.cuh"
 #include "lockstep.cuh"
 #include "models.cuh"
 #include "nuts_warp.cuh"
@@ -58,6 +59,9 @@ struct b200_model {
     EightSchoolsModel::Params eight{};
     RadonModel::Params radon{};
     StochVolModel::Params stochvol{};
+    const signed char* tr_kind = nullptr;  // per-element backward transforms (b200_model_set_transforms)
+    const double* tr_lo = nullptr;
+    const double* tr_hi = nullptr;
     IrModel::Params ir{};
     long long ir_max_obs = 0;
     void* ir_scratch = nullptr;   // per-team scratch of the generic IR device function: [slots][n_pad + max N] doubles
@@ -86,6 +90,12 @@ struct b200_model {
     const uint8_t* y8 = nullptr;    // LOGISTIC: y[N]
     long long n_rows = 0;
     int KP = 0;
+    // LOGISTIC, tensor-core performance mode (csrc/logistic_tc.cuh): fp16 hi/lo pieces of X and their TMA tensor maps
+    int precision = B200_PRECISION_FP64;
+    const __half* Xh = nullptr;
+    const __half* Xl = nullptr;
+    long long tc_slabs = 0;
+    CUtensorMap map_hi{}, map_lo{};
     // per-chain tree scratch of the persistent kernel, kept between runs (cudaMalloc/cudaFree of 100+ MB per call costs
     // tens of milliseconds of host time on the end-to-end path)
     void* scratch = nullptr;
@@ -136,6 +146,7 @@ extern "C" int b200_struct_size(int which) {
         case 10: return (int)sizeof(b200_ir_ar1);
         case 11: return (int)sizeof(b200_ir_param);
         case 12: return (int)sizeof(b200_ir_factor);
+        case 13: return (int)sizeof(b200_chain_state);
         default: return -1;
     }
 }
@@ -380,7 +391,7 @@ static int prepare_ir(b200_model* m, const b200_model_desc* d) {
             return fail("ir: likelihood %d needs sigma", l);
         for (int t = 0; t < L.n_terms; ++t) {
             const b200_ir_term& T = L.terms[t];
-            if (T.n_factors < 1 || T.n_factors > 3) return fail("ir: likelihood %d term %d: 1..3 variable factors", l, t);
+            if (T.n_factors < 0 || T.n_factors > 3) return fail("ir: likelihood %d term %d: 0..3 variable factors", l, t);
             IrTermD TD{};
             TD.n_factors = T.n_factors;
             if (T.coef && upload_raw(m, T.coef, (size_t)N, &TD.coef)) return -1;
@@ -457,6 +468,19 @@ extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) 
 }
 
 extern "C" void b200_model_destroy(b200_model* m) { delete m; }
+
+extern "C" int b200_model_set_transforms(b200_model* m, const int8_t* kind, const double* lo, const double* hi) {
+    if (!m || !kind || !lo || !hi) return fail("b200_model_set_transforms: null argument");
+    for (int i = 0; i < m->n; ++i) {
+        if (kind[i] < 0 || kind[i] > 2) return fail("b200_model_set_transforms: element %d: unknown transform %d", i, (int)kind[i]);
+        if (kind[i] == 2 && !(lo[i] < hi[i])) return fail("b200_model_set_transforms: element %d: interval needs lo < hi", i);
+    }
+    CU(cudaSetDevice(m->device));
+    std::vector<signed char> k(kind, kind + m->n);
+    std::vector<double> l(lo, lo + m->n), h(hi, hi + m->n);
+    if (upload(m, k, &m->tr_kind) || upload(m, l, &m->tr_lo) || upload(m, h, &m->tr_hi)) return -1;
+    return 0;
+}
 extern "C" int b200_model_n(const b200_model* m) { return m ? m->n : -1; }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,6 +779,65 @@ struct BatchScratch {  // logistic partial results
     int gx = 0, cpad = 0;
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core performance mode of the logistic GLM (tcgen05 + TMEM + TMA, split fp16): preparation and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*b200_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_x_map(CUtensorMap* map, const __half* base, long long rows) {
+    static b200_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<b200_encode_tiled_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)kTcK, (cuuint64_t)rows};       // innermost first: features, rows
+    const cuuint64_t strides[1] = {(cuuint64_t)kTcK * sizeof(__half)};     // row pitch in bytes
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTcRows};                   // 64 features (128 B) x 128 rows
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static int prepare_logistic_tc(b200_model* m) {
+    if (m->Xh) return 0;
+    m->tc_slabs = (m->n_rows + kTcRows - 1) / kTcRows;
+    const long long rows_pad = m->tc_slabs * kTcRows;
+    void *h = nullptr, *l = nullptr;
+    CU(cudaMalloc(&h, (size_t)rows_pad * kTcK * sizeof(__half)));
+    m->owned.push_back(h);
+    CU(cudaMalloc(&l, (size_t)rows_pad * kTcK * sizeof(__half)));
+    m->owned.push_back(l);
+    const long long total = rows_pad * kTcK;
+    logistic_tc_split_kernel<<<(unsigned)((total + 255) / 256), 256>>>(m->X, m->n_rows, m->n, m->KP, (__half*)h, (__half*)l, rows_pad);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    m->Xh = (const __half*)h;
+    m->Xl = (const __half*)l;
+    if (make_x_map(&m->map_hi, m->Xh, rows_pad) || make_x_map(&m->map_lo, m->Xl, rows_pad)) return -1;
+    return 0;
+}
+
+extern "C" int b200_model_set_precision(b200_model* m, int32_t mode) {
+    if (!m) return fail("b200_model_set_precision: null model");
+    if (mode != B200_PRECISION_FP64 && mode != B200_PRECISION_TC_FP16X2) return fail("b200_model_set_precision: unknown mode %d", mode);
+    if (mode == B200_PRECISION_TC_FP16X2) {
+        if (m->kind != B200_MODEL_LOGISTIC) return fail("tensor-core mode is implemented for the logistic GLM (dense design-matrix contraction) only");
+        CU(cudaSetDevice(m->device));
+        if (prepare_logistic_tc(m)) return -1;
+    }
+    m->precision = mode;
+    return 0;
+}
+
 static bool is_lockstep_kind(int kind) { return kind == B200_MODEL_MVGAUSS || kind == B200_MODEL_LOGISTIC; }
 
 template <int KB>
@@ -791,6 +874,17 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
         CU(bs.lpart.alloc((size_t)gx * bs.cpad * sizeof(double)));
     }
     int rc = 0;
+    if (m->precision == B200_PRECISION_TC_FP16X2) {
+        // tcgen05 path: the same partial-result layout ([gx][Cpad][128] fp64), so the fixed-order finish below is shared
+        if (m->KP != kTcK) {  // partials are [.][.][KP]: the tensor-core kernel writes 128-wide rows
+            return fail("tensor-core mode needs the 128-feature layout (65..128 features); this model has %d", m->n);
+        }
+        auto kern = logistic_tc_kernel;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        LogisticTcArgs A{m->y8, m->n_rows, m->tc_slabs, Q, ld, C, m->n, bs.gpart.as<double>(), bs.lpart.as<double>(), bs.cpad};
+        kern<<<dim3(bs.gx, bs.cpad / kLogiChains), kTcThreads, kTcSmemBytes, st>>>(m->map_hi, m->map_lo, A);
+        CU(cudaGetLastError());
+    } else
     switch (m->KP) {
         case 8: rc = launch_logistic<1>(m, C, Q, ld, bs, st); break;
         case 32: rc = launch_logistic<4>(m, C, Q, ld, bs, st); break;
@@ -900,7 +994,7 @@ struct NutsLaunch {
     int operator()(const typename Model::Params& MP) {
         constexpr int NP = 32 * W * NPL;
         constexpr bool SUBS = (W > 1) ? true : (B200_SUBTREE_SMEM != 0);
-        int wpb = (W == 1) ? env_int("B200_NUTS_WPB", 4) : 1;  // chains per CTA
+        int wpb = (W == 1) ? env_int("B200_NUTS_WPB", 8) : 1;  // chains per CTA (8 warps, 1 CTA per SM: measured best, r2)
         int hot = env_int("B200_NUTS_HOT", (W == 1) ? 2 : 1);
         wpb = std::max(1, std::min(wpb, B200_NUTS_THREADS / 32));
         hot = std::max(0, std::min(hot, P.max_td));
@@ -935,8 +1029,8 @@ struct NutsLaunch {
         const int blocks = std::max(1, std::min(need, std::max(1, per_sm) * sms));
         // iterations per work unit: fine enough to balance chains of different cost, coarse enough that the ~3 KB state
         // hand-over per unit is noise.  One unit per chain when every chain has its own resident team anyway.
-        const int Ttot = P.tune + P.draws;
-        int seg = env_int("B200_NUTS_SEG", 25);
+        const int Ttot = P.n_iter;
+        int seg = env_int("B200_NUTS_SEG", 50);  // measured (r2): 10 -> 390 ms, 25 -> 370, 50 -> 361, 100 -> 367
         if (seg <= 0 || need <= blocks) seg = Ttot;
         P.seg_iters = std::max(1, std::min(seg, Ttot));
         typename Model::Params MPl;
@@ -966,8 +1060,16 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     const bool lockstep = is_lockstep_kind(m->kind);
     if (cfg->mass_kind == B200_MASS_DENSE) {
         if (m->kind != B200_MODEL_MVGAUSS) return fail("b200_nuts_run: the dense mass matrix is the model's covariance (MVGAUSS only)");
+    } else if (cfg->mass_kind == B200_MASS_DIAG_ADAPT_GRAD) {
+        if (lockstep) return fail("b200_nuts_run: DIAG_ADAPT_GRAD is implemented by the persistent engine only");
+        if (!(cfg->mass_alpha > 0 && cfg->mass_alpha < 1)) return fail("b200_nuts_run: mass_alpha must be in (0, 1)");
     } else if (cfg->mass_kind != B200_MASS_DIAG && cfg->mass_kind != B200_MASS_DIAG_ADAPT) {
         return fail("b200_nuts_run: mass kind %d not implemented", cfg->mass_kind);
+    }
+    if (cfg->sampler != B200_SAMPLER_NUTS && cfg->sampler != B200_SAMPLER_HMC) return fail("b200_nuts_run: unknown sampler %d", cfg->sampler);
+    if (cfg->sampler == B200_SAMPLER_HMC) {
+        if (lockstep) return fail("b200_nuts_run: HamiltonianMC is implemented by the persistent engine only");
+        if (!(cfg->path_length > 0) || cfg->max_steps < 1) return fail("b200_nuts_run: HMC needs path_length > 0 and max_steps >= 1");
     }
     if (cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER && !z)
         return fail("b200_nuts_run: momentum_source=HOST_BUFFER but z is null");
@@ -976,8 +1078,17 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     CU(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    const long long Ttot = (long long)cfg->tune + cfg->draws;
-    const long long T = cfg->store_warmup ? Ttot : cfg->draws;
+    // iterations of this call: [it0, it0 + n_iter) of the chain's tune + draws schedule (default: all of it)
+    const long long Tsched = (long long)cfg->tune + cfg->draws;
+    const long long it0 = cfg->iter_begin;
+    if (it0 < 0 || it0 >= Tsched) return fail("b200_nuts_run: iter_begin %lld outside the schedule of %lld iterations", it0, Tsched);
+    const long long Ttot = cfg->iter_count > 0 ? cfg->iter_count : Tsched - it0;  // iterations run by this call
+    if (it0 + Ttot > Tsched) return fail("b200_nuts_run: iter_begin + iter_count exceeds tune + draws");
+    if ((it0 > 0) != (cfg->resume != nullptr)) return fail("b200_nuts_run: iter_begin > 0 needs `resume` (and only then)");
+    if ((cfg->resume || cfg->save || it0 > 0 || Ttot != Tsched) && lockstep)
+        return fail("b200_nuts_run: partial schedules / chain-state export are implemented by the persistent engine only");
+    const long long rec_lo = cfg->store_warmup ? it0 : std::max<long long>(cfg->tune, it0);
+    const long long T = std::max<long long>(0, it0 + Ttot - rec_lo);
     const size_t vb = (size_t)C * n * sizeof(double);
     Staged s_q0, s_var0, s_mean0, s_eps0, s_rng, s_z, s_draws;
     if (stage_in(s_q0, q0, vb, mem, true, false, st) || stage_in(s_var0, var0, vb, mem, true, false, st) ||
@@ -985,7 +1096,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         stage_in(s_eps0, eps0, (size_t)C * sizeof(double), mem, true, false, st) ||
         stage_in(s_rng, rng, (size_t)C * sizeof(b200_pcg64), mem, true, true, st) ||
         stage_in(s_z, cfg->momentum_source == B200_MOMENTUM_HOST_BUFFER ? z : nullptr, vb * Ttot, mem, true, false, st) ||
-        stage_in(s_draws, draws_out, vb * T, mem, false, true, st, /*direct=*/true))
+        stage_in(s_draws, T > 0 ? draws_out : nullptr, vb * T, mem, false, true, st, /*direct=*/true))
         return -1;
     // stats / summary arrays
     b200_stats ds{};
@@ -1024,7 +1135,30 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     }
     // draws of a frozen chain ("bad initial energy") from the failing iteration on are set to NaN by the kernels
 
+    // per-chain state in / out (b200_chain_state): 15 arrays each, staged like every other buffer
+    b200_chain_state d_resume{}, d_save{};
+    Staged st_state[30];
+    {
+        const size_t sb = (size_t)C * sizeof(double), ib = (size_t)C * sizeof(int32_t), lb = (size_t)C * sizeof(int64_t);
+        int slot = 0;
+        auto stage_state = [&](const b200_chain_state* src, b200_chain_state* dst, bool in) -> int {
+            if (!src) return 0;
+#define B200_SF(field, bytes, type)                                                                       \
+    if (!src->field) return fail("b200_nuts_run: chain state field `" #field "` is null");               \
+    if (stage_in(st_state[slot], src->field, bytes, mem, in, !in, st)) return -1;                        \
+    dst->field = (type*)st_state[slot++].ptr();
+            B200_SF(q, vb, double) B200_SF(log_step, sb, double) B200_SF(log_bar, sb, double) B200_SF(hbar, sb, double)
+            B200_SF(da_count, ib, int32_t) B200_SF(n_samples, ib, int32_t) B200_SF(window, ib, int32_t) B200_SF(var, vb, double)
+            B200_SF(fg_n, sb, double) B200_SF(fg_mean, vb, double) B200_SF(fg_m2, vb, double) B200_SF(bg_n, sb, double)
+            B200_SF(bg_mean, vb, double) B200_SF(bg_m2, vb, double) B200_SF(n_grad, lb, int64_t)
+#undef B200_SF
+            return 0;
+        };
+        if (stage_state(cfg->resume, &d_resume, true) || stage_state(cfg->save, &d_save, false)) return -1;
+    }
+
     NutsDev P{};
+    P.it0 = (int)it0; P.n_iter = (int)Ttot; P.resume = d_resume; P.save = d_save;
     P.C = C; P.n = n; P.tune = cfg->tune; P.draws = cfg->draws;
     P.max_td = cfg->max_treedepth; P.early_td = cfg->early_max_treedepth;
     P.adapt_step = cfg->adapt_step_size; P.mass_kind = cfg->mass_kind;
@@ -1034,10 +1168,16 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     P.target = cfg->target_accept; P.gamma = cfg->gamma; P.kappa = cfg->k; P.t0 = cfg->t0;
     P.Emax = cfg->Emax; P.init_weight = cfg->mass_initial_weight;
     P.philox_seed = cfg->philox_seed; P.chain_offset = cfg->chain_offset;
+    P.sampler = cfg->sampler; P.max_steps = cfg->max_steps; P.path_length = cfg->path_length;
+    P.mass_alpha = cfg->mass_alpha; P.stop_adaptation = cfg->stop_adaptation < 0 ? 0x7fffffff : cfg->stop_adaptation;
     P.q0 = (const double*)s_q0.ptr(); P.var0 = (const double*)s_var0.ptr();
     P.mean0 = (const double*)s_mean0.ptr(); P.eps0c = (const double*)s_eps0.ptr(); P.z = (const double*)s_z.ptr();
     P.rng = (b200_pcg64*)s_rng.ptr(); P.draws_out = (double*)s_draws.ptr();
     P.st = ds; P.sm = dsum;
+    if (cfg->constrain_draws) {
+        if (!m->tr_kind) return fail("b200_nuts_run: constrain_draws needs b200_model_set_transforms first");
+        P.tr_kind = m->tr_kind; P.tr_lo = m->tr_lo; P.tr_hi = m->tr_hi;
+    }
 
     if (lockstep) {
         LsDev Q{};
@@ -1049,6 +1189,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         Q.init_weight = P.init_weight; Q.philox_seed = P.philox_seed;
         Q.q0 = P.q0; Q.var0 = P.var0; Q.mean0 = P.mean0; Q.eps0c = P.eps0c; Q.z = P.z; Q.rng = P.rng;
         Q.draws_out = P.draws_out; Q.st = P.st; Q.sm = P.sm;
+        Q.tr_kind = P.tr_kind; Q.tr_lo = P.tr_lo; Q.tr_hi = P.tr_hi;
         if (run_lockstep(m, Q, st)) return -1;
     } else {
         NutsLaunch L{m, P, st};
@@ -1058,6 +1199,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     if (stage_out(s_rng, st) || stage_out(s_draws, st)) return -1;
     for (auto& s : st_arr) if (stage_out(s, st)) return -1;
     for (auto& s : sm_arr) if (stage_out(s, st)) return -1;
+    for (auto& s : st_state) if (stage_out(s, st)) return -1;
     CU(cudaStreamSynchronize(st));
     return 0;
 }

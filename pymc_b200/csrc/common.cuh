@@ -212,4 +212,18 @@ __device__ __forceinline__ void stats_sentinel(const b200_stats& st, long long o
     if (st.model_logp) st.model_logp[o] = qnan;
 }
 
+// Draw post-processing fused into the record step: the backward transform of one element, what the reference
+// evaluates per draw through a compiled function (backends/ndarray.py:108; transforms logprob/transforms.py:880-891,
+// :1026-1045).  kind == null: the unconstrained value is recorded.
+__device__ __forceinline__ double constrained(double q, int i, const signed char* kind, const double* lo, const double* hi) {
+    if (!kind) return q;
+    const int t = kind[i];
+    if (t == 1) return exp(q);
+    if (t == 2) {
+        const double s = sigmoid(q);
+        return s * hi[i] + (1.0 - s) * lo[i];
+    }
+    return q;
+}
+
 }  // namespace b200

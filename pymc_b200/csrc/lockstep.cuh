@@ -59,6 +59,7 @@ struct LsDev {
     const double* q0; const double* var0; const double* mean0; const double* eps0c; const double* z;
     b200_pcg64* rng;
     double* draws_out;
+    const signed char* tr_kind; const double* tr_lo; const double* tr_hi;  // record constrained values (common.cuh)
     b200_stats st;
     b200_chain_summary sm;
     LsState* state;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             const double qi = V(LV_PQ)[i];
             V(LV_Q)[i] = qi; V(LV_G)[i] = V(LV_PQG)[i];
             if (dense) V(LV_W)[i] = V(LV_PQW)[i];
-            if (rec) P.draws_out[((long long)chain * T_out + t_out) * n + i] = qi;
+            if (rec) P.draws_out[((long long)chain * T_out + t_out) * n + i] = constrained(qi, i, P.tr_kind, P.tr_lo, P.tr_hi);
         }
         S.cur_logp = S.m_plogp;
         if (adapting) {  // step_sizes.py:66-78

@@ -40,6 +40,10 @@ constexpr int kMaxLevels = 12;  // pending-subtree levels (max_treedepth <= 12)
 struct NutsDev {
     int C, n, tune, draws, max_td, early_td, adapt_step, mass_kind, momentum_source, store_warmup;
     int window, discard, hot_levels, chain_offset;
+    int it0, n_iter;                           // this call runs the iterations [it0, it0 + n_iter) of the chain's schedule
+    b200_chain_state resume, save;             // optional per-chain state in / out (null pointers: not used)
+    int sampler, max_steps, stop_adaptation;   // B200_SAMPLER_*; HMC: max leapfrogs; DIAG_ADAPT_GRAD: stop after this many
+    double path_length, mass_alpha;            // HMC trajectory length; DIAG_ADAPT_GRAD decay rate
     double eps0, target, gamma, kappa, t0, Emax, init_weight;
     unsigned long long philox_seed;
     const double* q0;     // [C][n]
@@ -49,6 +53,9 @@ struct NutsDev {
     const double* z;      // [C][Ttot][n] or null
     b200_pcg64* rng;      // [C]
     double* draws_out;    // [C][T][n]
+    const signed char* tr_kind;  // [n] or null: record CONSTRAINED values (0 identity, 1 exp, 2 lo + (hi - lo) sigmoid)
+    const double* tr_lo;         // [n]
+    const double* tr_hi;         // [n]
     b200_stats st;
     b200_chain_summary sm;
     double* scratch;            // per-chain global scratch
@@ -109,11 +116,9 @@ __host__ __device__ inline size_t nuts_warp_smem_bytes(int NP, int hot, bool sub
 #define B200_NUTS_MINBLOCKS 1  // __launch_bounds__ min CTAs/SM: the register budget knob
 #endif
 // W = warps per chain (team).  SUBS = subtree-under-construction vectors in shared memory instead of registers.
-#ifdef B200_NUTS_MAXREG  // A/B knob: an explicit register cap for the chain-per-warp kernels (cannot be combined with bounds)
-#define B200_NUTS_BOUNDS __maxnreg__(W > 1 ? 255 : B200_NUTS_MAXREG)
-#else
+// Register caps below the ~240 the kernel wants were measured and rejected (round 2, profiles/r2_variants.md): 224 registers
+// (9 warps/SM) 460 ms, 200 (10 warps/SM, 264 B of spills) 521 ms, 168 (12 warps/SM) 685 ms vs 370 ms at 2 x 4 warps per SM.
 #define B200_NUTS_BOUNDS __launch_bounds__(W > 1 ? 32 * W : B200_NUTS_THREADS, W > 1 ? 1 : B200_NUTS_MINBLOCKS)
-#endif
 template <class Model, int NPL, int W, bool SUBS>
 __global__ void B200_NUTS_BOUNDS
     nuts_warp_kernel(const NutsDev P, const typename Model::Params M) {
@@ -158,10 +163,11 @@ __global__ void B200_NUTS_BOUNDS
     double* sc_s = sc_pidx + kMaxLevels;
     double* red = sc_s + kMaxLevels;     // W x 8 doubles, cross-warp reductions (W > 1)
     const int n = P.n;
-    const int Ttot = P.tune + P.draws;
-    const int T_out = P.store_warmup ? Ttot : P.draws;
-    const int seg_iters = P.seg_iters > 0 ? P.seg_iters : Ttot;
-    const unsigned int n_seg = (unsigned int)((Ttot + seg_iters - 1) / seg_iters);
+    const int it_lo = P.it0, it_hi = P.it0 + P.n_iter;  // global iteration indices of this call
+    const int rec_lo = P.store_warmup ? it_lo : max(P.tune, it_lo);  // first recorded iteration
+    const int T_out = max(0, it_hi - rec_lo);
+    const int seg_iters = P.seg_iters > 0 ? P.seg_iters : P.n_iter;
+    const unsigned int n_seg = (unsigned int)((P.n_iter + seg_iters - 1) / seg_iters);
     const unsigned int n_units = n_seg * (unsigned int)P.C;
 
     // ---- work loop: one (chain, segment) unit per turn ---------------------------------------------------
@@ -180,7 +186,7 @@ __global__ void B200_NUTS_BOUNDS
     if (unit >= n_units) break;
     const int seg = (int)(unit / (unsigned int)P.C);
     const int chain = (int)(unit - (unsigned int)seg * (unsigned int)P.C);
-    const int it_begin = seg * seg_iters, it_end = min(Ttot, it_begin + seg_iters);
+    const int it_begin = it_lo + seg * seg_iters, it_end = min(it_hi, it_begin + seg_iters);
     if (seg > 0) {  // the chain's previous segment may still be running on another team (every thread acquires)
         while (ld_acquire_i32(P.done + chain) < seg) __nanosleep(64);
         team_sync<W>();
@@ -223,6 +229,24 @@ __global__ void B200_NUTS_BOUNDS
         da_count = 1;
         n_grad = 0;
         bad_at = -1;
+        if (P.resume.log_step) {  // continue a chain from an exported state (BaseHMC / potential / step_adapt sampling_state)
+            const b200_chain_state& R = P.resume;
+            log_step = R.log_step[chain]; log_bar = R.log_bar[chain]; hbar = R.hbar[chain]; da_count = R.da_count[chain];
+            k_samples = R.n_samples[chain]; window = R.window[chain];
+            fg_n = R.fg_n[chain]; bg_n = R.bg_n[chain]; n_grad = R.n_grad[chain];
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                const long long o = (long long)chain * n + i;
+                const bool in = i < n;
+                q_s[i] = in ? R.q[o] : 0.0;
+                VAR(k) = in ? R.var[o] : 1.0;
+                gvec(G_FGM)[i] = in ? R.fg_mean[o] : 0.0;
+                gvec(G_FGV)[i] = in ? R.fg_m2[o] : 0.0;
+                gvec(G_BGM)[i] = in ? R.bg_mean[o] : 0.0;
+                gvec(G_BGV)[i] = in ? R.bg_m2[o] : 0.0;
+            }
+        }
     } else {
         const ChainCtx cx = P.ctx[chain];
         fg_m = cx.fg_m; fg_v = cx.fg_v; bg_m = cx.bg_m; bg_v = cx.bg_v;
@@ -245,10 +269,55 @@ __global__ void B200_NUTS_BOUNDS
     }
     team_sync<W>();
 
+    // QuadPotentialDiagAdaptExp.update with use_grads (quadpotential.py:531-579); sample = q_s, grad = g_s.  The four
+    // Welford slots of the scratch hold (mean, var) of the draws and of the gradients.
+    auto grad_mass_update = [&](double* em, double* ev, double* gm, double* gv) {
+        if (k_samples >= P.stop_adaptation) return;
+        const double al = P.mass_alpha, om = 1.0 - P.mass_alpha;
+        if (k_samples > P.discard) {
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                double d = q_s[i] - em[i];
+                em[i] = __dadd_rn(em[i], __dmul_rn(al, d));
+                ev[i] = __dmul_rn(om, __dadd_rn(ev[i], __dmul_rn(al, __dmul_rn(d, d))));
+                d = g_s[i] - gm[i];
+                gm[i] = __dadd_rn(gm[i], __dmul_rn(al, d));
+                gv[i] = __dmul_rn(om, __dadd_rn(gv[i], __dmul_rn(al, __dmul_rn(d, d))));
+            }
+        } else if (k_samples == P.discard) {
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                em[i] = q_s[i]; ev[i] = 0.0; gm[i] = g_s[i]; gv[i] = 0.0;
+            }
+        }
+        if (k_samples > 2 * P.discard) {  // _update_from_variances :569-575: var = sqrt(var_draws / var_grads), no clipping
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                if (i < n) VAR(k) = sqrt(ev[i] / gv[i]);
+            }
+        }
+        ++k_samples;
+    };
+
     for (int it = it_begin; it < it_end && bad_at < 0; ++it) {
         const bool tuning = it < P.tune;
         const bool adapting = tuning && P.adapt_step;
 
+        // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75): the evaluation at q0 does not depend on
+        //      p0, so it runs first ...
+        team_sync<W>();
+        const double logp0 = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
+        team_sync<W>();
+        ++n_grad;
+        // ---- ... which lets QuadPotentialDiagAdaptExp.update(sample, grad) (quadpotential.py:531-567) of the PREVIOUS
+        //      iteration run here, where the accepted position's gradient is at hand (the reference calls it at the end of
+        //      astep, base_hmc.py:238, before the next potential.random(): same order of effects, no gradient carried
+        //      through the tree).  _ExpWeightedVariance.add_sample :465-469 with NumPy's unfused elementwise arithmetic.
+        if (P.mass_kind == B200_MASS_DIAG_ADAPT_GRAD && it > 0 && it - 1 < P.tune)
+            grad_mass_update(gvec(G_FGM), gvec(G_FGV), gvec(G_BGM), gvec(G_BGV));
         // ---- p0 = potential.random(): inv_std * z  (quadpotential.py:323-326, :617-619) ------------
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
@@ -256,16 +325,11 @@ __global__ void B200_NUTS_BOUNDS
             double zz = 0.0;
             if (i < n) {
                 zz = (P.momentum_source == B200_MOMENTUM_HOST_BUFFER)
-                         ? P.z[((long long)chain * Ttot + it) * n + i]
+                         ? P.z[((long long)chain * P.n_iter + (it - it_lo)) * n + i]
                          : philox_normal(P.philox_seed, (uint32_t)(chain + P.chain_offset), (uint32_t)it, (uint32_t)i);
             }
             p[k] = (1.0 / sqrt(VAR(k))) * zz;
         }
-        // ---- start = integrator.compute_state(q0, p0)  (integration.py:68-75) ----------------------
-        team_sync<W>();
-        const double logp0 = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
-        team_sync<W>();
-        ++n_grad;
         double kin = 0.0;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) kin = fma(p[k], VAR(k) * p[k], kin);
@@ -277,52 +341,27 @@ __global__ void B200_NUTS_BOUNDS
         const double eps = exp(adapting ? log_step : log_bar);  // step_adapt.current (step_sizes.py:60-64)
         const int maxd = (tuning && it < 200) ? P.early_td : P.max_td;  // nuts.py:205-208
 
-        // ---- _Tree.__init__ (nuts.py:292-332): both edges, proposal and p_sum are the start state ----
-        double* Lq = gvec(G_LQ); double* Lp = gvec(G_LP); double* Lg = gvec(G_LG);
-        double* Rq = gvec(G_RQ); double* Rp = gvec(G_RP); double* Rg = gvec(G_RG);
-        double* PSv = gvec(G_PS); double* PQv = gvec(G_PQ); double* NEARP = gvec(G_NEARP);
-#pragma unroll
-        for (int k = 0; k < NPL; ++k) {
-            const int i = lane + TS * k;
-            const double qi = q_s[i], gi = g_s[i];
-            Lq[i] = qi; Rq[i] = qi; PQv[i] = qi;
-            Lg[i] = gi; Rg[i] = gi;
-            Lp[i] = p[k]; Rp[i] = p[k]; PSv[i] = p[k];
-        }
-        int L_idx = 0, R_idx = 0;
         double m_logw = 0.0, m_pe = E0, m_plogp = logp0;
         double m_s = 1.0;
         int m_pidx = 0;
         double accept_sum = 0.0, max_de = 0.0;  // sum of min(1, exp(-dE)): exp(log_accept_sum) of nuts.py:415 without the log
         int n_prop = 0, depth = 0;
         bool diverged = false, turned = false, hit_max = false;
-
+        double hmc_accept = 0.0;
+        double* PQv = gvec(G_PQ);
         int d_iter = 0;
-        for (; d_iter < maxd; ++d_iter) {
-            const int dir = (rng.next_double() < 0.5) ? 1 : -1;  // nuts.py:215
-            // ---- load the edge we grow from into the integrator state; remember its p ----------------
-            const double* Eq = dir > 0 ? Rq : Lq;
-            const double* Ep = dir > 0 ? Rp : Lp;
-            const double* Eg = dir > 0 ? Rg : Lg;
-            int w_idx = dir > 0 ? R_idx : L_idx;
+        if (P.sampler == B200_SAMPLER_HMC) {
+            // ---- HamiltonianMC._hamiltonian_step (hmc/hmc.py:143-200): a fixed-length trajectory, Metropolis accept ----
+            d_iter = -1;  // no tree: `reached_max_treedepth` stays false
 #pragma unroll
-            for (int k = 0; k < NPL; ++k) {
-                const int i = lane + TS * k;
-                q_s[i] = Eq[i];
-                g_s[i] = Eg[i];
-                p[k] = Ep[i];
-                NEARP[i] = p[k];
-            }
-            const double es = dir * eps, dt = 0.5 * es;
-
-            // ---- _build_subtree(edge, depth, +-eps): 2^depth leaves, merges driven by a binary counter --
-            bool sub_div = false, sub_turn = false;
-            double c_logw = 0.0, c_pe = 0.0, c_plogp = 0.0;
-            double c_s = 1.0;
-            int c_pidx = 0;
-            const int n_leaf = 1 << depth;
-            for (int leaf = 0; leaf < n_leaf; ++leaf) {
-                // -- one leapfrog (integration.py:109-145)
+            for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = q_s[lane + TS * k];  // end = start unless accepted
+            // step_rand = unif (hmc.py:35-36, :141): Generator.uniform(0.85, 1.15) = low + (high - low) * next_double
+            const double es = (0.85 + (1.15 - 0.85) * rng.next_double()) * eps, dt = 0.5 * es;
+            const double ratio = P.path_length / es;
+            int n_steps = (ratio >= (double)P.max_steps) ? P.max_steps : (int)ratio;  // max(1, int(.)), min(max_steps, .)
+            if (n_steps < 1) n_steps = 1;
+            double logp = logp0, E = E0;
+            for (int sidx = 0; sidx < n_steps; ++sidx) {  // integrator.step (integration.py:109-145)
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int i = lane + TS * k;
@@ -330,209 +369,281 @@ __global__ void B200_NUTS_BOUNDS
                     q_s[i] = fma(es, VAR(k) * p[k], q_s[i]);
                 }
                 team_sync<W>();
-                const double logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
+                logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
                 team_sync<W>();
                 ++n_grad;
                 double kk = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + TS * k;
-                    p[k] = fma(dt, g_s[i], p[k]);
+                    p[k] = fma(dt, g_s[lane + TS * k], p[k]);
                     kk = fma(p[k], VAR(k) * p[k], kk);
                 }
-                const double E = 0.5 * team_sum<W>(kk, lane, red) - logp;
-                w_idx += dir;
-                // -- _single_step bookkeeping (nuts.py:406-440)
-                ++n_prop;
-                double dE = E - E0;
-                if (isnan(dE)) dE = INFINITY;
-                accept_sum += (dE > 0) ? exp(-dE) : 1.0;
-                if (fabs(dE) > fabs(max_de)) max_de = dE;
-                if (!(dE < P.Emax)) {
-                    sub_div = true;
-                    break;
-                }
-                // the leaf as a height-0 subtree: left = right = p_sum = p, proposal = itself
+                E = 0.5 * team_sum<W>(kk, lane, red) - logp;
+            }
+            n_prop = n_steps;
+            bool div = !isfinite(E);           // "Divergence encountered, bad energy."
+            double dE = E - E0;
+            if (isnan(dE)) dE = INFINITY;
+            if (fabs(dE) > P.Emax) div = true;  // two-sided, unlike NUTS (hmc.py:164)
+            hmc_accept = fmin(1.0, exp(-dE));
+            bool accepted = false;
+            if (!div) accepted = !(rng.next_double() >= hmc_accept);  // the uniform is drawn only without a divergence
+            if (accepted) {
 #pragma unroll
+                for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = q_s[lane + TS * k];
+                m_pidx = n_steps;
+            }
+            diverged = div; m_pe = E; m_plogp = logp; max_de = dE;  // stats report the trajectory's LAST state (hmc.py:180-188)
+        } else {
+            // ---- _Tree.__init__ (nuts.py:292-332): both edges, proposal and p_sum are the start state ----
+            double* Lq = gvec(G_LQ); double* Lp = gvec(G_LP); double* Lg = gvec(G_LG);
+            double* Rq = gvec(G_RQ); double* Rp = gvec(G_RP); double* Rg = gvec(G_RG);
+            double* PSv = gvec(G_PS); double* NEARP = gvec(G_NEARP);
+    #pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const int i = lane + TS * k;
+                const double qi = q_s[i], gi = g_s[i];
+                Lq[i] = qi; Rq[i] = qi; PQv[i] = qi;
+                Lg[i] = gi; Rg[i] = gi;
+                Lp[i] = p[k]; Rp[i] = p[k]; PSv[i] = p[k];
+            }
+            int L_idx = 0, R_idx = 0;
+            for (; d_iter < maxd; ++d_iter) {
+                const int dir = (rng.next_double() < 0.5) ? 1 : -1;  // nuts.py:215
+                // ---- load the edge we grow from into the integrator state; remember its p ----------------
+                const double* Eq = dir > 0 ? Rq : Lq;
+                const double* Ep = dir > 0 ? Rp : Lp;
+                const double* Eg = dir > 0 ? Rg : Lg;
+                int w_idx = dir > 0 ? R_idx : L_idx;
+    #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
-                    LP(k) = p[k];
-                    PS(k) = p[k];
-                    PQ(k) = q_s[lane + TS * k];
+                    const int i = lane + TS * k;
+                    q_s[i] = Eq[i];
+                    g_s[i] = Eg[i];
+                    p[k] = Ep[i];
+                    NEARP[i] = p[k];
                 }
-                c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
-                c_s = 1.0;
+                const double es = dir * eps, dt = 0.5 * es;
 
-                // -- merge with pending left siblings while the counter carries (nuts.py:452-476)
-                int h = 0;
-                for (int m = leaf; m & 1; m >>= 1, ++h) {
-                    const double* t_ps = lvl(h, 2);
-                    const double* t_lp = h ? lvl(h, 0) : t_ps;
-                    const double* t_rp = h ? lvl(h, 1) : t_ps;
-                    double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    if (h == 0) {
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + TS * k;
-                            const double tp = t_ps[i];
-                            const double s = tp + PS(k);
-                            dots[0] = fma(s, VAR(k) * tp, dots[0]);
-                            dots[1] = fma(s, VAR(k) * p[k], dots[1]);
-                            LP(k) = tp;
-                            PS(k) = s;
-                        }
-                        double d2[2] = {dots[0], dots[1]};
-                        team_sum_n<W>(d2, lane, red);
-                        dots[0] = d2[0]; dots[1] = d2[1];
-                        dots[2] = dots[3] = dots[4] = dots[5] = 1.0;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + TS * k;
-                            const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
-                            const double s = tp + PS(k);
-                            const double vl = VAR(k) * tl, vr = VAR(k) * p[k];
-                            dots[0] = fma(s, vl, dots[0]);
-                            dots[1] = fma(s, vr, dots[1]);
-                            const double s1 = tp + LP(k);  // tree1.p_sum + tree2.left.p
-                            dots[2] = fma(s1, vl, dots[2]);
-                            dots[3] = fma(s1, VAR(k) * LP(k), dots[3]);
-                            const double s2 = tr + PS(k);  // tree1.right.p + tree2.p_sum
-                            dots[4] = fma(s2, VAR(k) * tr, dots[4]);
-                            dots[5] = fma(s2, vr, dots[5]);
-                            LP(k) = tl;
-                            PS(k) = s;
-                        }
-                    }
-                    if (h) team_sum_n<W>(dots, lane, red);
-                    const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
-                                      (dots[4] <= 0) || (dots[5] <= 0);
-                    // weights (m, s): tree1 = (sc_logw[h], sc_s[h]), tree2 = (c_logw, c_s); P(pick tree2) = w2 / (w1 + w2)
-                    const double t_m = sc_logw[h], t_s = sc_s[h];
-                    const double dm = c_logw - t_m;
-                    const double e_w = exp(-fabs(dm));
-                    const double w2 = (dm >= 0.0) ? c_s : c_s * e_w, w1 = (dm >= 0.0) ? t_s * e_w : t_s;
-                    const double ws = w1 + w2;
-                    const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
-                    if (!(u * ws < w2)) {  // keep tree1's proposal
-                        const double* t_pq = lvl(h, 3);
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + TS * k];
-                        c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
-                    }
-                    c_logw = fmax(c_logw, t_m);
-                    c_s = ws;
-                    if (turn) {
-                        sub_turn = true;
-                        break;
-                    }
-                }
-                if (sub_turn) break;
-                // -- not the last leaf: park the subtree (height h) until its right sibling is built
-                if (leaf + 1 < n_leaf) {
-                    double* s_ps = lvl(h, 2);
-                    double* s_pq = lvl(h, 3);
-                    if (h == 0) {
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + TS * k;
-                            s_ps[i] = PS(k);
-                            s_pq[i] = PQ(k);
-                        }
-                    } else {
-                        double* s_lp = lvl(h, 0);
-                        double* s_rp = lvl(h, 1);
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            const int i = lane + TS * k;
-                            s_lp[i] = LP(k);
-                            s_rp[i] = p[k];
-                            s_ps[i] = PS(k);
-                            s_pq[i] = PQ(k);
-                        }
-                    }
-                    if (lane == 0) {
-                        sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
-                        sc_s[h] = c_s;
+                // ---- _build_subtree(edge, depth, +-eps): 2^depth leaves, merges driven by a binary counter --
+                bool sub_div = false, sub_turn = false;
+                double c_logw = 0.0, c_pe = 0.0, c_plogp = 0.0;
+                double c_s = 1.0;
+                int c_pidx = 0;
+                const int n_leaf = 1 << depth;
+                for (int leaf = 0; leaf < n_leaf; ++leaf) {
+                    // -- one leapfrog (integration.py:109-145)
+    #pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        const int i = lane + TS * k;
+                        p[k] = fma(dt, g_s[i], p[k]);
+                        q_s[i] = fma(es, VAR(k) * p[k], q_s[i]);
                     }
                     team_sync<W>();
+                    const double logp = Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
+                    team_sync<W>();
+                    ++n_grad;
+                    double kk = 0.0;
+    #pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        const int i = lane + TS * k;
+                        p[k] = fma(dt, g_s[i], p[k]);
+                        kk = fma(p[k], VAR(k) * p[k], kk);
+                    }
+                    const double E = 0.5 * team_sum<W>(kk, lane, red) - logp;
+                    w_idx += dir;
+                    // -- _single_step bookkeeping (nuts.py:406-440)
+                    ++n_prop;
+                    double dE = E - E0;
+                    if (isnan(dE)) dE = INFINITY;
+                    accept_sum += (dE > 0) ? exp(-dE) : 1.0;
+                    if (fabs(dE) > fabs(max_de)) max_de = dE;
+                    if (!(dE < P.Emax)) {
+                        sub_div = true;
+                        break;
+                    }
+                    // the leaf as a height-0 subtree: left = right = p_sum = p, proposal = itself
+    #pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        LP(k) = p[k];
+                        PS(k) = p[k];
+                        PQ(k) = q_s[lane + TS * k];
+                    }
+                    c_logw = -dE; c_pe = E; c_plogp = logp; c_pidx = w_idx;
+                    c_s = 1.0;
+
+                    // -- merge with pending left siblings while the counter carries (nuts.py:452-476)
+                    int h = 0;
+                    for (int m = leaf; m & 1; m >>= 1, ++h) {
+                        const double* t_ps = lvl(h, 2);
+                        const double* t_lp = h ? lvl(h, 0) : t_ps;
+                        const double* t_rp = h ? lvl(h, 1) : t_ps;
+                        double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        if (h == 0) {
+    #pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                const int i = lane + TS * k;
+                                const double tp = t_ps[i];
+                                const double s = tp + PS(k);
+                                dots[0] = fma(s, VAR(k) * tp, dots[0]);
+                                dots[1] = fma(s, VAR(k) * p[k], dots[1]);
+                                LP(k) = tp;
+                                PS(k) = s;
+                            }
+                            double d2[2] = {dots[0], dots[1]};
+                            team_sum_n<W>(d2, lane, red);
+                            dots[0] = d2[0]; dots[1] = d2[1];
+                            dots[2] = dots[3] = dots[4] = dots[5] = 1.0;
+                        } else {
+    #pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                const int i = lane + TS * k;
+                                const double tl = t_lp[i], tr = t_rp[i], tp = t_ps[i];
+                                const double s = tp + PS(k);
+                                const double vl = VAR(k) * tl, vr = VAR(k) * p[k];
+                                dots[0] = fma(s, vl, dots[0]);
+                                dots[1] = fma(s, vr, dots[1]);
+                                const double s1 = tp + LP(k);  // tree1.p_sum + tree2.left.p
+                                dots[2] = fma(s1, vl, dots[2]);
+                                dots[3] = fma(s1, VAR(k) * LP(k), dots[3]);
+                                const double s2 = tr + PS(k);  // tree1.right.p + tree2.p_sum
+                                dots[4] = fma(s2, VAR(k) * tr, dots[4]);
+                                dots[5] = fma(s2, vr, dots[5]);
+                                LP(k) = tl;
+                                PS(k) = s;
+                            }
+                        }
+                        if (h) team_sum_n<W>(dots, lane, red);
+                        const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
+                                          (dots[4] <= 0) || (dots[5] <= 0);
+                        // weights (m, s): tree1 = (sc_logw[h], sc_s[h]), tree2 = (c_logw, c_s); P(pick tree2) = w2 / (w1 + w2)
+                        const double t_m = sc_logw[h], t_s = sc_s[h];
+                        const double dm = c_logw - t_m;
+                        const double e_w = exp(-fabs(dm));
+                        const double w2 = (dm >= 0.0) ? c_s : c_s * e_w, w1 = (dm >= 0.0) ? t_s * e_w : t_s;
+                        const double ws = w1 + w2;
+                        const double u = rng.next_double();  // drawn whenever both halves succeeded (nuts.py:466)
+                        if (!(u * ws < w2)) {  // keep tree1's proposal
+                            const double* t_pq = lvl(h, 3);
+    #pragma unroll
+                            for (int k = 0; k < NPL; ++k) PQ(k) = t_pq[lane + TS * k];
+                            c_pe = sc_pe[h]; c_plogp = sc_plogp[h]; c_pidx = (int)sc_pidx[h];
+                        }
+                        c_logw = fmax(c_logw, t_m);
+                        c_s = ws;
+                        if (turn) {
+                            sub_turn = true;
+                            break;
+                        }
+                    }
+                    if (sub_turn) break;
+                    // -- not the last leaf: park the subtree (height h) until its right sibling is built
+                    if (leaf + 1 < n_leaf) {
+                        double* s_ps = lvl(h, 2);
+                        double* s_pq = lvl(h, 3);
+                        if (h == 0) {
+    #pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                const int i = lane + TS * k;
+                                s_ps[i] = PS(k);
+                                s_pq[i] = PQ(k);
+                            }
+                        } else {
+                            double* s_lp = lvl(h, 0);
+                            double* s_rp = lvl(h, 1);
+    #pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                const int i = lane + TS * k;
+                                s_lp[i] = LP(k);
+                                s_rp[i] = p[k];
+                                s_ps[i] = PS(k);
+                                s_pq[i] = PQ(k);
+                            }
+                        }
+                        if (lane == 0) {
+                            sc_logw[h] = c_logw; sc_pe[h] = c_pe; sc_plogp[h] = c_plogp; sc_pidx[h] = (double)c_pidx;
+                            sc_s[h] = c_s;
+                        }
+                        team_sync<W>();
+                    }
                 }
-            }
-            ++depth;  // nuts.py:365 (counts the aborted doubling too)
-            if (sub_div || sub_turn) {
-                diverged = sub_div;
-                turned = sub_turn;
-                break;
-            }
-            // ---- the new outer edge is the integrator state (self.right/left = tree.right) ------------
-            {
-                double* Nq = dir > 0 ? Rq : Lq;
-                double* Np = dir > 0 ? Rp : Lp;
-                double* Ng = dir > 0 ? Rg : Lg;
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + TS * k;
-                    Nq[i] = q_s[i];
-                    Ng[i] = g_s[i];
-                    Np[i] = p[k];
-                }
-                if (dir > 0) R_idx = w_idx; else L_idx = w_idx;
-            }
-            // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
-            {
-                // accept the new subtree's proposal iff u < w_new / w_old  (log(u) < log_size_new - log_size_old)
-                const double u = rng.next_double();
-                const double dm = c_logw - m_logw;
-                const double e_w = exp(-fabs(dm));
-                const double wn = (dm >= 0.0) ? c_s : c_s * e_w, wo = (dm >= 0.0) ? m_s * e_w : m_s;
-                if (u * wo < wn) {
-#pragma unroll
-                    for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = PQ(k);
-                    m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
-                }
-                m_logw = fmax(c_logw, m_logw);
-                m_s = wo + wn;
-            }
-            // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
-            {
-                const double* FARP = dir > 0 ? Lp : Rp;
-                double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) {
-                    const int i = lane + TS * k;
-                    const double so = PSv[i], fp = FARP[i], np_ = NEARP[i];
-                    const double s = so + PS(k);
-                    PSv[i] = s;
-                    const double vf = VAR(k) * fp, vw = VAR(k) * p[k];
-                    dots[0] = fma(s, vf, dots[0]);
-                    dots[1] = fma(s, vw, dots[1]);
-                    const double a = so + LP(k);   // old p_sum + (new subtree's edge adjacent to the old tree).p
-                    dots[2] = fma(a, vf, dots[2]);
-                    dots[3] = fma(a, VAR(k) * LP(k), dots[3]);
-                    const double b = np_ + PS(k);  // (old tree's edge adjacent to the new subtree).p + new p_sum
-                    dots[4] = fma(b, VAR(k) * np_, dots[4]);
-                    dots[5] = fma(b, vw, dots[5]);
-                }
-                team_sum_n<W>(dots, lane, red);
-                if ((dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) || (dots[4] <= 0) ||
-                    (dots[5] <= 0)) {
-                    turned = true;
+                ++depth;  // nuts.py:365 (counts the aborted doubling too)
+                if (sub_div || sub_turn) {
+                    diverged = sub_div;
+                    turned = sub_turn;
                     break;
+                }
+                // ---- the new outer edge is the integrator state (self.right/left = tree.right) ------------
+                {
+                    double* Nq = dir > 0 ? Rq : Lq;
+                    double* Np = dir > 0 ? Rp : Lp;
+                    double* Ng = dir > 0 ? Rg : Lg;
+    #pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        const int i = lane + TS * k;
+                        Nq[i] = q_s[i];
+                        Ng[i] = g_s[i];
+                        Np[i] = p[k];
+                    }
+                    if (dir > 0) R_idx = w_idx; else L_idx = w_idx;
+                }
+                // ---- biased progressive pick (nuts.py:370-374), drawn before the full-tree U-turn checks --
+                {
+                    // accept the new subtree's proposal iff u < w_new / w_old  (log(u) < log_size_new - log_size_old)
+                    const double u = rng.next_double();
+                    const double dm = c_logw - m_logw;
+                    const double e_w = exp(-fabs(dm));
+                    const double wn = (dm >= 0.0) ? c_s : c_s * e_w, wo = (dm >= 0.0) ? m_s * e_w : m_s;
+                    if (u * wo < wn) {
+    #pragma unroll
+                        for (int k = 0; k < NPL; ++k) PQv[lane + TS * k] = PQ(k);
+                        m_pe = c_pe; m_plogp = c_plogp; m_pidx = c_pidx;
+                    }
+                    m_logw = fmax(c_logw, m_logw);
+                    m_s = wo + wn;
+                }
+                // ---- U-turn checks on the whole tree (nuts.py:376-390) ------------------------------------
+                {
+                    const double* FARP = dir > 0 ? Lp : Rp;
+                    double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    #pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        const int i = lane + TS * k;
+                        const double so = PSv[i], fp = FARP[i], np_ = NEARP[i];
+                        const double s = so + PS(k);
+                        PSv[i] = s;
+                        const double vf = VAR(k) * fp, vw = VAR(k) * p[k];
+                        dots[0] = fma(s, vf, dots[0]);
+                        dots[1] = fma(s, vw, dots[1]);
+                        const double a = so + LP(k);   // old p_sum + (new subtree's edge adjacent to the old tree).p
+                        dots[2] = fma(a, vf, dots[2]);
+                        dots[3] = fma(a, VAR(k) * LP(k), dots[3]);
+                        const double b = np_ + PS(k);  // (old tree's edge adjacent to the new subtree).p + new p_sum
+                        dots[4] = fma(b, VAR(k) * np_, dots[4]);
+                        dots[5] = fma(b, vw, dots[5]);
+                    }
+                    team_sum_n<W>(dots, lane, red);
+                    if ((dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) || (dots[4] <= 0) ||
+                        (dots[5] <= 0)) {
+                        turned = true;
+                        break;
+                    }
                 }
             }
         }
         if (d_iter == maxd) hit_max = !tuning;  // for/else of nuts.py:220-221
 
         // ---- the accepted position becomes the chain state -------------------------------------------
-        const double accept = accept_sum / n_prop;  // nuts.py:479
+        const double accept = (P.sampler == B200_SAMPLER_HMC) ? hmc_accept : accept_sum / n_prop;  // nuts.py:479
         const bool rec = P.store_warmup || !tuning;
-        const int t_out = P.store_warmup ? it : it - P.tune;
+        const int t_out = it - rec_lo;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + TS * k;
             const double qi = PQv[i];
             q_s[i] = qi;
             PQ(k) = qi;
-            if (rec && i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = qi;
+            if (rec && i < n) P.draws_out[((long long)chain * T_out + t_out) * n + i] = constrained(qi, i, P.tr_kind, P.tr_lo, P.tr_hi);
         }
         // ---- step_adapt.update (step_sizes.py:66-78); products/sums kept unfused like the Python scalars
         if (adapting) {
@@ -599,7 +710,7 @@ __global__ void B200_NUTS_BOUNDS
             if (P.st.step_size_bar) P.st.step_size_bar[o] = exp(log_bar);
             if (P.st.mean_tree_accept) P.st.mean_tree_accept[o] = accept;
             if (P.st.energy) P.st.energy[o] = m_pe;
-            if (P.st.energy_error) P.st.energy_error[o] = m_pe - E0;
+            if (P.st.energy_error) P.st.energy_error[o] = (P.sampler == B200_SAMPLER_HMC) ? max_de : m_pe - E0;
             if (P.st.max_energy_error) P.st.max_energy_error[o] = max_de;
             if (P.st.model_logp) P.st.model_logp[o] = m_plogp;
         }
@@ -611,7 +722,7 @@ __global__ void B200_NUTS_BOUNDS
     if (bad_at >= 0) {
         for (int t = max(bad_at, it_begin); t < it_end; ++t) {
             if (!(P.store_warmup || t >= P.tune)) continue;
-            const int t_out = P.store_warmup ? t : t - P.tune;
+            const int t_out = t - rec_lo;
 #pragma unroll
             for (int k = 0; k < NPL; ++k) {
                 const int i = lane + TS * k;
@@ -622,7 +733,7 @@ __global__ void B200_NUTS_BOUNDS
     }
     // ---- end of the segment: the stream position goes back to the caller's array (it is also where the next segment
     //      picks it up); last segment: adaptation results; otherwise: the chain's state for the next segment ------------
-    const bool last_seg = it_end >= Ttot;
+    const bool last_seg = it_end >= it_hi;
     if (lane == 0) {
         b200_pcg64 r;
         r.state_hi = (uint64_t)(rng.state >> 64); r.state_lo = (uint64_t)rng.state;
@@ -640,7 +751,33 @@ __global__ void B200_NUTS_BOUNDS
             P.ctx[chain] = cx;
         }
     }
+    if (last_seg && P.save.log_step) {  // export the chain's state (the pending DIAG_ADAPT_GRAD update stays pending)
+        const b200_chain_state& S = P.save;
+        if (lane == 0) {
+            S.log_step[chain] = log_step; S.log_bar[chain] = log_bar; S.hbar[chain] = hbar; S.da_count[chain] = da_count;
+            S.n_samples[chain] = k_samples; S.window[chain] = window;
+            S.fg_n[chain] = fg_n; S.bg_n[chain] = bg_n; S.n_grad[chain] = n_grad;
+        }
+        const double* fm = gvec(fg_m); const double* fv = gvec(fg_v); const double* bm = gvec(bg_m); const double* bv = gvec(bg_v);
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int i = lane + TS * k;
+            if (i < n) {
+                const long long o = (long long)chain * n + i;
+                S.q[o] = q_s[i]; S.var[o] = VAR(k);
+                S.fg_mean[o] = fm[i]; S.fg_m2[o] = fv[i]; S.bg_mean[o] = bm[i]; S.bg_m2[o] = bv[i];
+            }
+        }
+    }
     if (last_seg) {
+        if (P.mass_kind == B200_MASS_DIAG_ADAPT_GRAD && it_hi >= P.tune + P.draws && P.draws == 0 && bad_at < 0 && P.sm.final_var &&
+            !P.save.log_step) {
+            // the update that follows the last tuning iteration needs that position's gradient: one more evaluation
+            team_sync<W>();
+            (void)Model::template eval<NPL, W, true>(M, data_s, q_s, g_s, lane, red);
+            team_sync<W>();
+            grad_mass_update(gvec(G_FGM), gvec(G_FGV), gvec(G_BGM), gvec(G_BGV));
+        }
         if (P.sm.final_var) {
 #pragma unroll
             for (int k = 0; k < NPL; ++k) {

@@ -29,6 +29,26 @@ def _ir_spec(ir) -> ModelSpec:
     return ModelSpec(models.KIND_IR, n, vars_, data={}, meta={"initial_point": ir.initial_point(), "ir": ir})
 
 
+class ChainState:
+    """Per-chain sampler state between calls (b200_chain_state; BaseHMC.sampling_state of the reference, hmc/base_hmc.py:61-71
+    with step_sizes.py:26-38 and quadpotential.py:189-208, :396-403): host NumPy arrays, one row per chain."""
+
+    def __init__(self, chains: int, n: int):
+        self.chains, self.n = chains, n
+        for name, dt, vec in _lib.STATE_FIELDS:
+            setattr(self, name, np.zeros((chains, n) if vec else (chains,), dtype=dt))
+        self.iter_count = 0  # iterations completed (the `iter_begin` of the next call)
+
+    def c_struct(self):
+        st = _lib.ChainStateC()
+        for name, _, _ in _lib.STATE_FIELDS:
+            setattr(st, name, getattr(self, name).ctypes.data)
+        return st
+
+    def as_dict(self):
+        return {name: getattr(self, name).copy() for name, _, _ in _lib.STATE_FIELDS} | {"iter_count": self.iter_count}
+
+
 class CompiledModel:
     """Observed data resident in HBM + dispatch to the model's fused logp/grad device function.
 
@@ -88,6 +108,24 @@ class CompiledModel:
         handle = C.c_void_p()
         _lib.check(self._lib.b200_model_create(C.byref(d), C.byref(handle)))
         self._h = handle
+        # backward transforms per element, for draws recorded in constrained space (nuts_run(constrain=True))
+        kind, lo, hi = np.zeros(spec.n, dtype=np.int8), np.zeros(spec.n), np.ones(spec.n)
+        for v in spec.vars:
+            sl = slice(v.offset, v.offset + v.size)
+            if v.transform == "log":
+                kind[sl] = 1
+            elif v.transform == "interval":
+                kind[sl], lo[sl], hi[sl] = 2, v.bounds[0], v.bounds[1]
+        self.supports_constrain = hasattr(self._lib, "b200_model_set_transforms")
+        if self.supports_constrain:
+            _lib.check(self._lib.b200_model_set_transforms(self._h, kind.ctypes.data, lo.ctypes.data, hi.ctypes.data))
+
+    def set_precision(self, mode: str) -> None:
+        """"fp64" (parity mode, default) or "tc_fp16x2": the dense contractions of the logistic GLM on the tcgen05 tensor
+        cores with split-fp16 operands (performance mode; gradient ~1e-7 relative, see include/b200nuts.h)."""
+        code = {"fp64": _lib.PRECISION_FP64, "tc_fp16x2": _lib.PRECISION_TC_FP16X2}[mode]
+        _lib.check(self._lib.b200_model_set_precision(self._h, code))
+        self.precision = mode
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -140,9 +178,16 @@ class CompiledModel:
                  mass="diag_adapt", adapt_step_size=True, step_scale=0.25, target_accept=0.8, gamma=0.05,
                  k=0.75, t0=10.0, Emax=1000.0, max_treedepth=10, early_max_treedepth=8,
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
-                 device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False, reuse_outputs=False):
+                 device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False, reuse_outputs=False,
+                 sampler="nuts", path_length=2.0, max_steps=1024, mass_alpha=0.02, stop_adaptation=None, constrain=False,
+                 iter_begin=0, iter_count=None, resume=None, save=None):
         """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
 
+        ``sampler="hmc"`` runs HamiltonianMC (hmc/hmc.py: ``path_length``, ``max_steps``; pass ``target_accept=0.65`` for
+        its default); ``mass="diag_adapt_grad"`` is init="jitter+adapt_diag_grad" (``mass_alpha``, ``stop_adaptation``).
+        ``iter_begin`` / ``iter_count`` run a slice of the ``tune + draws`` schedule; ``resume`` / ``save`` are ``ChainState``
+        objects (host arrays) carrying the chains between calls: a run split into slices is bit-identical to the
+        uninterrupted run (persistent engine; outputs and ``z`` then cover the slice only).
         ``rng_states``: structured array (``_lib.PCG64_DTYPE``) of the chains' NumPy PCG64 step streams
         (see ``pymc_b200.rng``); updated in place.  ``z``: optional momentum noise [C, tune+draws, n]
         (NumPy ``Generator.normal`` for draw-parity with the reference); otherwise generated on device.
@@ -155,13 +200,33 @@ class CompiledModel:
         if not is_torch(q0):
             q0 = _f64(q0).reshape(-1, self.n)
         Cn = q0.shape[0]
-        Ttot = tune + draws
-        T = Ttot if store_warmup else draws
+        n_iter = (tune + draws - iter_begin) if iter_count is None else int(iter_count)
+        Ttot = n_iter  # iterations of THIS call (z and the outputs cover exactly these)
+        rec_lo = iter_begin if store_warmup else max(tune, iter_begin)
+        T = max(0, iter_begin + n_iter - rec_lo)
         cfg = _lib.NutsCfg()
         cfg.chains, cfg.tune, cfg.draws = Cn, int(tune), int(draws)
         cfg.max_treedepth, cfg.early_max_treedepth = int(max_treedepth), int(early_max_treedepth)
         cfg.adapt_step_size = int(bool(adapt_step_size))
-        cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT, "dense": _lib.MASS_DENSE}[mass]
+        cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT, "dense": _lib.MASS_DENSE,
+                         "diag_adapt_grad": _lib.MASS_DIAG_ADAPT_GRAD}[mass]
+        cfg.sampler = {"nuts": _lib.SAMPLER_NUTS, "hmc": _lib.SAMPLER_HMC}[sampler]
+        cfg.path_length, cfg.max_steps = float(path_length), int(max_steps)
+        cfg.mass_alpha = float(mass_alpha)
+        cfg.stop_adaptation = -1 if stop_adaptation is None else int(stop_adaptation)
+        cfg.iter_begin, cfg.iter_count = int(iter_begin), int(n_iter)
+        keep_state = []
+        if resume is not None or save is not None:
+            if device_outputs:
+                raise ValueError("chain-state import/export uses host arrays: call with device_outputs=False")
+            for obj, name in ((resume, "resume"), (save, "save")):
+                if obj is not None:
+                    if obj.chains != Cn or obj.n != self.n:
+                        raise ValueError(f"{name}: ChainState is for {obj.chains} chains x {obj.n}, this call has {Cn} x {self.n}")
+                    cs = obj.c_struct()
+                    keep_state.append(cs)
+                    setattr(cfg, name, C.addressof(cs))
+        cfg.constrain_draws = int(bool(constrain))  # draws come back in CONSTRAINED space (transform fused into the record step)
         cfg.momentum_source = _lib.MOMENTUM_DEVICE_PHILOX if z is None else _lib.MOMENTUM_HOST_BUFFER
         cfg.store_warmup = int(bool(store_warmup))
         cfg.chain_offset = int(chain_offset)
@@ -247,6 +312,8 @@ class CompiledModel:
         )
         if device_outputs:
             rng_states[:] = rng_b.cpu().numpy().view(np.uint64).reshape(Cn, 4).view(_lib.PCG64_DTYPE).reshape(Cn)
+        if save is not None:
+            save.iter_count = iter_begin + n_iter
         ms, launches = _lib.last_kernel_ms()
         return NutsResult(draws=draws_b, stats=st_arr, summary=sm_arr, kernel_ms=ms, launches=launches,
                           tune=tune, n_draws=draws, store_warmup=store_warmup)

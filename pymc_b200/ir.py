@@ -165,8 +165,8 @@ class ModelIR:
                 raise ValueError(f"likelihood {L.dist!r} is not in the closed set {sorted(LIK_DISTS)}")
             N = len(L.y)
             for t in L.terms:
-                if not (1 <= len(t.factors) <= MAX_TERM_FACTORS):
-                    raise ValueError(f"a term has 1..{MAX_TERM_FACTORS} variable factors")
+                if len(t.factors) > MAX_TERM_FACTORS:  # no factor: a constant offset coef[i]
+                    raise ValueError(f"a term has at most {MAX_TERM_FACTORS} variable factors")
                 for vn, idx in t.factors:
                     v = self.var(vn)
                     if idx is None and v.size not in (1, N):

@@ -86,6 +86,14 @@ class ModelSpec:
             out[v.rv_name] = x
         return out
 
+    def split_rv(self, x: np.ndarray) -> dict[str, np.ndarray]:
+        """Already-constrained draws ``x[..., n]`` (recorded that way by the kernel) -> named RVs."""
+        out = {}
+        for v in self.vars:
+            a = x[..., v.offset : v.offset + v.size]
+            out[v.rv_name] = a[..., 0] if v.size == 1 else a
+        return out
+
     def initial_point(self) -> np.ndarray:
         """The model's default initial point in unconstrained space (support point of every prior,
         transformed; pymc/initial_point.py).  All five configs have support points that map to 0

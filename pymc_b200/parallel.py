@@ -41,8 +41,10 @@ def my_chain_range(chains: int) -> tuple[int, int]:
     return chain_range(chains, rank(), world_size())
 
 
-def gather_chains(draws, stats: dict, chains: int):
-    """All-gather per-rank shards [c_r, T, ...] into [chains, T, ...] on every rank.
+def gather_chains(draws, stats: dict, chains: int, dst: int | None = 0):
+    """Gather per-rank shards [c_r, T, ...] into [chains, T, ...] on rank ``dst`` (other ranks get ``(None, None)``);
+    ``dst=None`` all-gathers to every rank (N x the traffic and memory: 24 GB per rank for the Radon bench at 8 GPUs --
+    only when every rank really needs every draw).
 
     NCCL needs device tensors and equal shard shapes: shards are padded to the largest block."""
     import torch
@@ -60,12 +62,20 @@ def gather_chains(draws, stats: dict, chains: int):
         if t.shape[0] < cmax:
             pad = torch.zeros((cmax - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
             t = torch.cat([t, pad], dim=0)
-        outs = [torch.empty_like(t) for _ in range(world)]
-        d.all_gather(outs, t.contiguous())
+        if dst is None:
+            outs = [torch.empty_like(t) for _ in range(world)]
+            d.all_gather(outs, t.contiguous())
+        else:
+            outs = [torch.empty_like(t) for _ in range(world)] if d.get_rank() == dst else None
+            d.gather(t.contiguous(), outs, dst=dst)
+            if outs is None:
+                return None
         full = torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
         return full.cpu().numpy() if was_np else full
 
-    return gather(draws), {k: gather(v) for k, v in stats.items()}
+    g = gather(draws)
+    st = {k: gather(v) for k, v in stats.items()}
+    return (g, st) if g is not None else (None, None)
 
 
 def max_over_ranks(x: float) -> float:
@@ -91,3 +101,66 @@ def sum_over_ranks(x: float) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     d.all_reduce(t, op=d.ReduceOp.SUM)
     return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Pooled warm-up (north_star: "NCCL used only to gather draws and pooled warmup statistics at tuning-window boundaries").
+# An OPT-IN extension: the reference adapts every chain's mass matrix from its own draws only (quadpotential.py:335-355).
+# With thousands of chains the per-chain estimate (~100 draws per window) is the noisy part of warm-up and makes step sizes
+# -- hence tree depths and run times -- differ between chains; pooling the Welford statistics of all chains (and all GPUs)
+# at the window boundaries gives every chain the same, far better, estimate.
+# ------------------------------------------------------------------------------------------------------------------------
+def pool_welford(count, mean, m2):
+    """Combine per-chain Welford triples (count[C], mean[C, n], m2[C, n]) over the chains of ALL ranks (Chan et al.):
+    returns (N, mean[n], M2[n]).  One all-reduce of 2n + 1 doubles when torch.distributed is initialised."""
+    count = np.asarray(count, dtype=np.float64)
+    s0 = count.sum()
+    s1 = (count[:, None] * mean).sum(axis=0)
+    s2 = (m2 + count[:, None] * mean * mean).sum(axis=0)
+    d = _dist()
+    if d:
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if d.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.as_tensor(np.concatenate([[s0], s1, s2]), device=dev)
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+        t = t.cpu().numpy()
+        n = len(s1)
+        s0, s1, s2 = t[0], t[1 : 1 + n], t[1 + n :]
+    mu = s1 / s0
+    return float(s0), mu, s2 - s0 * mu * mu
+
+
+def pooled_warmup_run(cm, q0, rng_states, *, tune, draws, mean0=None, window=101, discard_window=50, chain_offset=0,
+                      philox_seed=0, **kw):
+    """NUTS/HMC run whose diagonal mass matrix is adapted from the POOLED draws of all chains of all ranks.
+
+    The tuning phase runs in slices that end at the reference's window boundaries (every ``window`` draws); inside a
+    slice the kernel only accumulates the per-chain estimators (draws after ``discard_window``, like the reference); at a
+    boundary the foreground estimators are pooled (``pool_welford``: one small all-reduce over NCCL), every chain's
+    inverse mass becomes the pooled variance, and foreground <- background as in the reference.  Chains are carried
+    between slices by ``engine.ChainState`` (the kernel continues them bit-exactly).  Returns the ``NutsResult`` of the
+    sampling phase with ``summary['final_var']`` = the pooled mass matrix."""
+    from . import engine
+
+    q0 = np.ascontiguousarray(q0, dtype=np.float64)
+    C, n = q0.shape
+    never = 1 << 30  # no in-kernel refresh / estimator switch: the host does both at the boundaries
+    common = dict(tune=tune, draws=draws, mass="diag_adapt", adaptation_window=never, discard_window=discard_window,
+                  chain_offset=chain_offset, philox_seed=philox_seed, **kw)
+    bounds = list(range(window + 1, tune, window)) + [tune] if tune > 0 else []
+    state, begin = None, 0
+    for b in bounds:
+        nxt = engine.ChainState(C, n)
+        cm.nuts_run(q0, rng_states, mean0=mean0, store_warmup=False, iter_begin=begin, iter_count=b - begin, resume=state,
+                    save=nxt, stats=False, **common)
+        state, begin = nxt, b
+        if state.fg_n.min() > 0:
+            N, mu, M2 = pool_welford(state.fg_n, state.fg_mean, state.fg_m2)
+            state.var[:] = np.clip(M2 / N, 1e-12, 1e12)[None, :]
+        # foreground <- background, background starts empty (QuadPotentialDiagAdapt.update, quadpotential.py:350-354)
+        state.fg_n[:], state.fg_mean[:], state.fg_m2[:] = state.bg_n, state.bg_mean, state.bg_m2
+        state.bg_n[:], state.bg_mean[:], state.bg_m2[:] = 0.0, 0.0, 0.0
+    res = cm.nuts_run(q0, rng_states, mean0=mean0, store_warmup=False, iter_begin=begin, iter_count=tune + draws - begin,
+                      resume=state, **common)
+    return res

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import rng as brng
 from .engine import CompiledModel
+from .ir import ModelIR
 from .models import ModelSpec
 
 
@@ -50,11 +51,20 @@ class SampleResult:
     warmup_posterior: dict | None = None
     warmup_sample_stats: dict | None = None
     attrs: dict = field(default_factory=dict)
+    observed_data: dict = field(default_factory=dict)   # groups external samplers are held to (test_mcmc_external.py:78-85)
+    constant_data: dict = field(default_factory=dict)
+
+    def groups(self):
+        out = ["posterior", "sample_stats"]
+        out += [g for g in ("observed_data", "constant_data") if getattr(self, g)]
+        out += [g for g in ("warmup_posterior", "warmup_sample_stats") if getattr(self, g) is not None]
+        return out
 
     def to_arviz(self):
         import arviz as az  # optional
 
-        return az.from_dict(posterior=self.posterior, sample_stats=self.sample_stats, attrs=self.attrs)
+        return az.from_dict(posterior=self.posterior, sample_stats=self.sample_stats, observed_data=self.observed_data or None,
+                            constant_data=self.constant_data or None, attrs=self.attrs)
 
 
 def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, jitter=True, logp_fn=None,
@@ -100,11 +110,11 @@ def sample_b200_nuts(
     *,
     tune: int = 1000,
     chains: int = 4,
-    target_accept: float = 0.8,
+    target_accept: float | None = None,
     random_seed=None,
     initvals=None,
     jitter: bool = True,
-    model: ModelSpec | CompiledModel | None = None,
+    model: ModelSpec | ModelIR | CompiledModel | None = None,
     var_names=None,
     nuts_kwargs: dict | None = None,
     progressbar: bool = False,
@@ -116,35 +126,72 @@ def sample_b200_nuts(
     discard_tuned_samples: bool = True,
     momentum: str = "device",
     nuts_sampler: str = "b200",
+    init: str = "auto",
+    step: str = "nuts",
+    gather: str = "rank0",
 ) -> SampleResult:
-    """Draw samples from the posterior using the B200 NUTS engine (init = ``jitter+adapt_diag``).
+    """Draw samples from the posterior using the B200 engine.
 
-    Arguments follow ``sample_jax_nuts``.  ``nuts_kwargs`` accepts the ``pm.NUTS`` keywords
-    ``max_treedepth, early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size``.
+    Arguments follow ``sample_jax_nuts`` (pymc/sampling/jax.py:495-517).  ``model``: a ``pymc_b200.ir.ModelIR`` (any model
+    of the closed factor set; ``from_pymc`` lowers a ``pm.Model`` to one), a ``ModelSpec`` naming a hand-written kernel, or
+    a ``CompiledModel``.  ``nuts_kwargs`` accepts the ``pm.NUTS`` / ``pm.HamiltonianMC`` keywords ``max_treedepth,
+    early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size, path_length, max_steps``.
+    ``init`` (pm.sample / init_nuts, pymc/sampling/mcmc.py:1759-2021): "auto" = "jitter+adapt_diag"; "adapt_diag";
+    "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250).
+    ``step``: "nuts" (target_accept default 0.8) or "hmc" (HamiltonianMC, default 0.65).
     ``momentum="numpy"`` draws the momentum normals from each chain's NumPy potential stream exactly like
     the reference (host-generated, uploaded); ``"device"`` generates them on the GPU (Philox).
+    Multi-GPU (torch.distributed initialised, one process per GPU): chains are sharded over the ranks; ``gather="rank0"``
+    collects all chains on rank 0 (the other ranks return their own shard, ``attrs["chains_held"]`` says which),
+    ``"all"`` gives every rank everything (world-size times the traffic), ``"none"`` leaves the posterior sharded.
+    Posterior values are constrained ON THE DEVICE where each draw is recorded (the backward transform is fused into the
+    kernel); ``keep_untransformed=True`` records the unconstrained positions and transforms on the host instead.
     """
     if model is None:
-        raise TypeError("model is required (a pymc_b200.models.ModelSpec or a CompiledModel)")
+        raise TypeError("model is required (a pymc_b200.ir.ModelIR, a pymc_b200.models.ModelSpec or a CompiledModel)")
     if chain_method not in ("vectorized", "parallel"):
         raise ValueError("chain_method must be 'vectorized' or 'parallel'")
+    if step not in ("nuts", "hmc"):
+        raise ValueError("step must be 'nuts' or 'hmc'")
     cm = model if hasattr(model, "nuts_run") else CompiledModel(model)  # a CompiledModel (or an object with its interface)
     spec = cm.spec
     nk = dict(nuts_kwargs or {})
+    if target_accept is None:
+        target_accept = 0.8 if step == "nuts" else 0.65  # base_hmc.py:91 / hmc.py:142
     nk.setdefault("target_accept", target_accept)
-    mass = nk.pop("mass", "diag_adapt")  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
+    if step == "hmc":
+        nk["sampler"] = "hmc"
+    if init == "auto":
+        init = "jitter+adapt_diag"
+    if init.startswith("jitter+"):
+        init = init[len("jitter+"):]
+    else:
+        jitter = False
+    if init == "adapt_diag":
+        mass = "diag_adapt"
+    elif init == "adapt_diag_grad":
+        mass = "diag_adapt_grad"
+        nk.setdefault("mass_alpha", 0.02)
+        nk.setdefault("stop_adaptation", tune - 50 if tune > 250 else None)  # mcmc.py:1900-1903
+    else:
+        raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag and (jitter+)adapt_diag_grad")
+    mass = nk.pop("mass", mass)  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
 
     from . import parallel
 
     lo, hi = parallel.my_chain_range(chains)
     step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(random_seed, chains)
     q0_all = initial_points(spec, chains, jitter_seeds, initvals, jitter, cm.logp_dlogp)
-    # init_nuts "jitter+adapt_diag": mean start point over ALL chains as the Welford prior mean (mcmc.py:1890-1894)
+    # init_nuts: mean start point over ALL chains as the estimator's prior mean (mcmc.py:1890-1894)
     mean0 = np.broadcast_to(q0_all.mean(axis=0), (hi - lo, spec.n)).copy()
     states = brng.pack_pcg64(step_rngs[lo:hi])
     z = brng.momentum_noise(pot_rngs[lo:hi], tune + draws, spec.n) if momentum == "numpy" else None
     # Philox key of the device momentum noise: an independent child of the root seed (never a function of a chain's jitter)
     seed_key = brng.philox_key(random_seed) if z is None else 0
+    # draws recorded in constrained space by the kernel itself (engines that implement `constrain`; test stand-ins do not)
+    on_device = (not keep_untransformed) and getattr(cm, "supports_constrain", False)
+    if on_device:
+        nk["constrain"] = True
 
     t0 = time.perf_counter()
     res = cm.nuts_run(q0_all[lo:hi], states, tune=tune, draws=draws, mean0=mean0, z=z, philox_seed=seed_key,
@@ -156,13 +203,18 @@ def sample_b200_nuts(
         raise SamplingError(f"Bad initial energy in chain {lo + c} at iteration {int(bad[c])}: check any log "
                             "probabilities that are inf or nan (model.debug())")
     d_all, st_all = res.draws, res.stats
-    if parallel.world_size() > 1:
-        d_all, st_all = parallel.gather_chains(d_all, st_all, chains)
+    held = (lo, hi)
+    if parallel.world_size() > 1 and gather != "none":
+        if gather not in ("rank0", "all"):
+            raise ValueError("gather must be 'rank0', 'all' or 'none'")
+        g_d, g_st = parallel.gather_chains(d_all, st_all, chains, dst=None if gather == "all" else 0)
+        if g_d is not None:
+            d_all, st_all, held = g_d, g_st, (0, chains)
 
     w = tune if not discard_tuned_samples else 0
 
     def pack(dq, st):
-        post = spec.constrain(dq)
+        post = spec.split_rv(dq) if on_device else spec.constrain(dq)
         if var_names is not None:
             post = {k: v for k, v in post.items() if k in var_names}
         stats = {_STAT_RENAME[k]: (v.astype(bool) if v.dtype == np.uint8 else v) for k, v in st.items()}
@@ -170,11 +222,18 @@ def sample_b200_nuts(
 
     post, stats = pack(d_all[:, w:], {k: v[:, w:] for k, v in st_all.items()})
     out = SampleResult(post, stats, d_all[:, w:] if keep_untransformed else None)
+    ir = getattr(cm, "ir", None)
+    if ir is not None:
+        out.observed_data, out.constant_data = ir.observed_data(), ir.constant_data()
+    elif getattr(spec, "data", None):
+        obs = {"y"}
+        out.observed_data = {k: np.asarray(v) for k, v in spec.data.items() if k in obs}
+        out.constant_data = {k: np.asarray(v) for k, v in spec.data.items() if k not in obs and np.ndim(v) == 1}
     if w:
         out.warmup_posterior, out.warmup_sample_stats = pack(d_all[:, :w], {k: v[:, :w] for k, v in st_all.items()})
-    out.attrs = {"sampling_time": sampling_time, "tuning_steps": tune, "inference_library": "pymc_b200",
+    out.attrs = {"sampling_time": sampling_time, "tuning_steps": tune, "inference_library": "pymc_b200", "chains_held": held,
                  "kernel_ms": res.kernel_ms, "grad_evals": int(st_all["tree_size"].sum())}
-    if compute_convergence_checks and chains > 1 and draws >= 8:
+    if compute_convergence_checks and d_all.shape[0] > 1 and draws >= 8:
         from . import diagnostics
 
         out.attrs["ess_bulk_min"], out.attrs["rhat_max"] = diagnostics.convergence_summary(d_all[:, w:])

@@ -201,9 +201,7 @@ class B200NUTS:
 
 
 def from_pymc(model):
-    """Lower a ``pm.Model`` to a ``ModelSpec``.  Not implemented this round: PyMC/PyTensor are
-    not importable in this image, so the lowering cannot be exercised; use ``pymc_b200.models`` specs."""
-    raise NotImplementedError(
-        "from_pymc: graph lowering is not implemented yet; build a pymc_b200.models.ModelSpec "
-        "(eight_schools(), radon(), ...) and pass it as model="
-    )
+    """Lower a ``pm.Model`` to a ``pymc_b200.ir.ModelIR``: see ``pymc_b200.frontend``."""
+    from .frontend import from_pymc as _from_pymc
+
+    return _from_pymc(model)

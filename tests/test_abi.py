@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # field order/size of the ctypes mirrors (a mismatch would corrupt arguments silently)
     assert ctypes.sizeof(_lib.Pcg64State) == 32 and _lib.PCG64_DTYPE.itemsize == 32
-    assert ctypes.sizeof(_lib.NutsCfg) == 10 * 4 + 7 * 8 + 2 * 4 + 8
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.NutsCfg) == lib.b200_struct_size(1) == 176 and ctypes.sizeof(_lib.ChainStateC) == lib.b200_struct_size(13)
     assert ctypes.sizeof(_lib.Stats) == 12 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.ChainSummary) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert _lib.ModelDesc.n_obs.offset == 8 and _lib.ModelDesc.x.offset == 24

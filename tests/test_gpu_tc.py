@@ -1,0 +1,127 @@
+"""-m gpu: the tensor-core performance mode of the logistic GLM (tcgen05.mma + TMEM + TMA, split fp16; csrc/logistic_tc.cuh)
+against the fp64 parity path and the oracle.  SURVEY section 7 ("fp64 parity vs tensor cores"): the performance mode states
+its measured error next to its throughput -- both land in gpurun_out/parity_report.json (copied to profiles/).
+
+Tolerances: gradient <= 1e-6 of its largest entry per chain (north_star's logp/grad bound), logp <= 1e-8 relative;
+sampler level: the fixed-step golden keeps its tree statistics, and an adaptive run's posterior agrees with the fp64
+run's within Monte Carlo error.
+"""
+import numpy as np
+import pytest
+
+from b200_helpers import discrete_equal, gpu_free_run
+from test_gpu_fullsize import _report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair128():
+    from pymc_b200 import engine, models
+
+    spec = models.logistic(n_rows=8192, n_features=128, seed=3)
+    a, b = engine.CompiledModel(spec), engine.CompiledModel(spec)
+    b.set_precision("tc_fp16x2")
+    return a, b
+
+
+def _errs(lp, g, lp_ref, g_ref):
+    scale = np.max(np.abs(g_ref), axis=1, keepdims=True)
+    return float(np.max(np.abs(g - g_ref) / scale)), float(np.max(np.abs(lp - lp_ref) / np.abs(lp_ref)))
+
+
+def test_tc_logp_grad_error_small_matrix(pair128):
+    """130 chains (two chain-CTAs, the second nearly empty), 64 slabs per chain block: four drains of the fp32 accumulator."""
+    from oracle import logp_numpy
+
+    cm64, cmtc = pair128
+    rng = np.random.default_rng(0)
+    Q = rng.normal(0.0, 0.4, (130, 128))
+    lp64, g64 = cm64.logp_dlogp(Q)
+    lptc, gtc = cmtc.logp_dlogp(Q)
+    f = logp_numpy.make_logp(cm64.spec)
+    lo = np.array([f(q)[0] for q in Q[:8]])
+    go = np.array([f(q)[1] for q in Q[:8]])
+    eg, el = _errs(lptc, gtc, lp64, g64)
+    eg_o, el_o = _errs(lptc[:8], gtc[:8], lo, go)
+    _report("tc_fp16x2/8192x128", {"grad_rel_to_max_vs_fp64": eg, "logp_rel_vs_fp64": el, "grad_rel_vs_oracle": eg_o,
+                                   "logp_rel_vs_oracle": el_o, "chains": 130})
+    assert eg <= 1e-6 and el <= 1e-8, (eg, el)
+    assert eg_o <= 1e-6 and el_o <= 1e-8, (eg_o, el_o)
+    lptc2, gtc2 = cmtc.logp_dlogp(Q)  # deterministic
+    assert np.array_equal(lptc, lptc2) and np.array_equal(gtc, gtc2)
+
+
+def test_tc_ragged_rows_and_few_features():
+    """N not a multiple of 128 (masked tail rows) and K < 128 but > 64 (zero-padded feature columns)."""
+    from pymc_b200 import engine, models
+
+    spec = models.logistic(n_rows=1000, n_features=100, seed=8)
+    a, b = engine.CompiledModel(spec), engine.CompiledModel(spec)
+    b.set_precision("tc_fp16x2")
+    Q = np.random.default_rng(1).normal(0.0, 0.5, (5, 100))
+    eg, el = _errs(*b.logp_dlogp(Q), *a.logp_dlogp(Q))
+    assert eg <= 1e-6 and el <= 1e-8, (eg, el)
+
+
+def test_tc_full_design_matrix_error_and_speed():
+    """BASELINE config #3's matrix (1e6 x 128), 512 chains: error of the performance mode and both kernels' time."""
+    from pymc_b200 import _lib, engine, models
+
+    spec = models.logistic()
+    cm = engine.CompiledModel(spec)
+    rng = np.random.default_rng(2)
+    Q = rng.normal(0.0, 0.3, (512, 128))
+    cm.logp_dlogp(Q)
+    lp64, g64 = cm.logp_dlogp(Q)
+    ms64, _ = _lib.last_kernel_ms()
+    cm.set_precision("tc_fp16x2")
+    cm.logp_dlogp(Q)
+    lptc, gtc = cm.logp_dlogp(Q)
+    mstc, _ = _lib.last_kernel_ms()
+    eg, el = _errs(lptc, gtc, lp64, g64)
+    flops = 4.0 * 1e6 * 128 * 512
+    _report("tc_fp16x2/1e6x128_512chains", {
+        "grad_rel_to_max_vs_fp64": eg, "logp_rel_vs_fp64": el, "fp64_dmma_ms": ms64, "tc_ms": mstc, "speedup": ms64 / mstc,
+        "fp64_equivalent_tflops_tc": flops / (mstc * 1e-3) / 1e12, "fp64_tflops_dmma": flops / (ms64 * 1e-3) / 1e12,
+        "tensor_flops_issued_tflops": 3 * flops / (mstc * 1e-3) / 1e12})
+    assert eg <= 1e-6 and el <= 1e-8, (eg, el)
+    assert ms64 / mstc >= 3.0, (ms64, mstc)
+
+
+def test_tc_fixed_step_golden_keeps_its_trees(pair128, golden):
+    name = "logistic_k128_fixed"
+    d = golden(name)
+    res, _ = gpu_free_run(pair128[1], d, name)
+    same = []
+    for c in range(len(d["seeds"])):
+        st = {k: v[c] for k, v in res.stats.items()}
+        same.append(discrete_equal(st, d, c))
+    same = np.concatenate(same)
+    err = float(np.max(np.abs(res.draws - d["draws_q"])))
+    _report("tc_fp16x2/fixed_step_golden", {"identical_tree_fraction": float(same.mean()), "draws": int(same.size),
+                                            "max_abs_position_error": err})
+    assert same.mean() >= 0.95
+    assert err <= 1e-4
+
+
+def test_tc_adaptive_run_posterior_matches_fp64_run(pair128):
+    from pymc_b200 import rng as brng
+
+    out = []
+    C = 64
+    for cm in pair128:
+        sr, _, js = brng.chain_generators(31, C)
+        q0 = np.stack([np.random.default_rng(s).uniform(-1, 1, 128) for s in js])
+        res = cm.nuts_run(q0, brng.pack_pcg64(sr), tune=150, draws=100, mean0=np.broadcast_to(q0.mean(0), q0.shape).copy(),
+                          store_warmup=False, philox_seed=77)
+        assert np.all(res.summary["bad_energy_at"] == -1)
+        out.append(res)
+    a, b = (r.draws.reshape(-1, 128) for r in out)
+    se = np.sqrt(a.var(0) / 1500 + b.var(0) / 1500)
+    z = np.abs(a.mean(0) - b.mean(0)) / se
+    _report("tc_fp16x2/adaptive_posterior", {"max_z_mean_vs_fp64_run": float(z.max()),
+                                             "evals_fp64": int(out[0].stats["tree_size"].sum()),
+                                             "evals_tc": int(out[1].stats["tree_size"].sum())})
+    assert z.max() < 5.0
+    assert np.all(np.abs(np.log(a.std(0) / b.std(0))) < 0.2)

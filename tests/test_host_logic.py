@@ -101,9 +101,20 @@ WORKER = textwrap.dedent(
     lo, hi = parallel.my_chain_range(chains)
     full = np.arange(chains * T * n, dtype=np.float64).reshape(chains, T, n)
     stats = {{"tree_size": (np.arange(chains * T, dtype=np.int32).reshape(chains, T))[lo:hi]}}
-    d, s = parallel.gather_chains(full[lo:hi].copy(), stats, chains)
+    d, s = parallel.gather_chains(full[lo:hi].copy(), stats, chains, dst=None)   # every rank gets everything
     assert np.array_equal(d, full), d
     assert np.array_equal(s["tree_size"], np.arange(chains * T, dtype=np.int32).reshape(chains, T))
+    d0, s0 = parallel.gather_chains(full[lo:hi].copy(), stats, chains)            # default: rank 0 only
+    if dist.get_rank() == 0:
+        assert np.array_equal(d0, full) and np.array_equal(s0["tree_size"], np.arange(chains * T, dtype=np.int32).reshape(chains, T))
+    else:
+        assert d0 is None and s0 is None
+    # pooled Welford over the chains of both ranks equals the single-process pooling
+    rs = np.random.default_rng(5)
+    cnt, mu, m2 = rs.integers(5, 50, chains).astype(float), rs.standard_normal((chains, n)), rs.random((chains, n)) * 10
+    N, pm_, pM2 = parallel.pool_welford(cnt[lo:hi], mu[lo:hi], m2[lo:hi])
+    N1 = cnt.sum(); m1 = (cnt[:, None] * mu).sum(0) / N1; M1 = (m2 + cnt[:, None] * (mu - m1) ** 2).sum(0)
+    assert abs(N - N1) < 1e-12 and np.allclose(pm_, m1, rtol=1e-13) and np.allclose(pM2, M1, rtol=1e-11)
     assert parallel.max_over_ranks(float(dist.get_rank())) == 1.0
     assert parallel.sum_over_ranks(1.5) == 3.0
     dist.destroy_process_group()

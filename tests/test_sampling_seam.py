@@ -66,9 +66,16 @@ WORKER = textwrap.dedent(
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
     spec = models.eight_schools()
     res = sampling.sample_b200_nuts(12, tune=25, chains=5, random_seed=3, model=OracleEngine(spec), momentum="numpy",
-                                    keep_untransformed=True)
+                                    keep_untransformed=True, gather="all")
     np.save(sys.argv[2], res.unconstrained)
-    assert res.sample_stats["n_steps"].shape == (5, 12)
+    assert res.sample_stats["n_steps"].shape == (5, 12) and res.attrs["chains_held"] == (0, 5)
+    r0 = sampling.sample_b200_nuts(12, tune=25, chains=5, random_seed=3, model=OracleEngine(spec), momentum="numpy",
+                                   keep_untransformed=True)  # default: all chains on rank 0, the others keep their shard
+    if dist.get_rank() == 0:
+        assert np.array_equal(r0.unconstrained, res.unconstrained)
+    else:
+        lo, hi = r0.attrs["chains_held"]
+        assert (lo, hi) != (0, 5) and np.array_equal(r0.unconstrained, res.unconstrained[lo:hi])
     dist.destroy_process_group()
     print("ok")
     """

@@ -83,6 +83,8 @@ def parse():
     ap.add_argument("--tune", type=int, default=-1)
     ap.add_argument("--draws", type=int, default=-1)
     ap.add_argument("--cpu-chains", type=int, default=0, help="reference arm / cpu_baseline: chains per step (0 = host cores)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "tc_fp16x2"],
+                    help="logistic only: fp64 DMMA (parity mode) or the tcgen05 split-fp16 tensor-core performance mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -394,6 +396,10 @@ def b200_arm(args):
     wl = args.wl
     spec = models.BUILDERS[wl["builder"]](**wl["args"])
     cm = engine.CompiledModel(spec, device=local)
+    if args.precision != "fp64":
+        if args.workload != "logistic":
+            raise SystemExit("--precision tc_fp16x2 applies to --workload logistic")
+        cm.set_precision(args.precision)
     tune, draws, n = args.tune, args.draws, spec.n
     if wl["scaling"] == "strong":  # fixed total number of chains, split over the ranks (BASELINE config #5)
         chains_total = args.chains_per_gpu * world if args.chains_per_gpu else wl["chains"]
@@ -505,6 +511,24 @@ def b200_arm(args):
             dmma = tf.value
     roofline = make_roofline(args.workload, wl, per_launch, k_ms, fp64, dmma, measured_peaks(),
                              ncu_traffic(args.workload, per_launch))
+    if args.precision == "tc_fp16x2":
+        # tensor-core performance mode: every fp64 product is three fp16 MMAs (hi*hi, hi*lo, lo*hi) -> issued tensor flops =
+        # 3 x the algorithmic 4 N K per eval; peak = the dense bf16/fp16 rate in MEASURED_PEAKS.json (sustained figure: the
+        # kernel runs inside a long loop), else the nominal 2250
+        issued = 3.0 * wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12
+        tpeak, tsrc = 2250.0, "nominal dense bf16/fp16 (MEASURED_PEAKS.json absent)"
+        try:
+            mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(mp_.get("bf16_tflops_sustained") or mp_["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak,
+                    "traffic": None, "peak_source": tsrc, "kernel": "logistic_tc_kernel (tcgen05.mma kind::f16, TMEM, TMA)",
+                    "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "issued_tensor_flops_per_eval": 3.0 * wl["per_eval"],
+                    "fp64_equivalent_tflops": wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12,
+                    "accuracy": "gradient <= 1e-6 of its largest entry, logp <= 1e-8 relative vs the fp64 path "
+                                "(tests/test_gpu_tc.py; profiles/r2_parity_report.json)",
+                    "time_base": "kernel_ms spans every launch of the lock-step loop (advance kernels and ragged tail included)"}
 
     # ---- cpu_baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -----------
     cpu = None
@@ -516,8 +540,10 @@ def b200_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if args.precision == "fp64" else "f16x2 split operands, f32 accumulate, f64 drains (performance mode)",
+            "data": "synthetic",
             "config": {"workload": workload_name(args, C if wl["scaling"] == "weak" else chains_total), **wl["desc"],
+                       "precision": args.precision,
                        "chains_per_gpu": C, "chains_total": chains_total, "tune": tune, "draws": draws,
                        "init": "jitter+adapt_diag" if wl["mass"] == "diag_adapt" else "jitter, fixed dense mass matrix",
                        "momentum": "device philox", "l2": wl["l2"]},

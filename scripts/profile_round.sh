@@ -23,6 +23,9 @@ if [ "$PART" = bench ]; then
   cap nuts nuts_warp_kernel 0 scripts/ncu_target_radon.py
   timeout -k 10 300 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $O/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_launches_bench.log 2>&1
   echo "launch list rc=$?"
+elif [ "$PART" = tc ]; then
+  timeout -k 10 200 $NCU --metrics gpu__time_duration.sum -c 300 --csv --log-file $O/${R}_launches_logistic_tc.csv python scripts/ncu_target3.py logistic_tc 4 2 > $O/${R}_launches_logistic_tc.log 2>&1
+  cap logistic_tc logistic_tc_kernel 2 scripts/ncu_target3.py logistic_tc 2 1
 elif [ "$PART" = stochvol ]; then
   cap stochvol nuts_warp_kernel 0 scripts/ncu_target_stochvol.py
 else

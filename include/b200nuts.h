@@ -292,6 +292,13 @@ void b200_model_destroy(b200_model* model);
  * b200_nuts_cfg.constrain_draws is set.  Replaces the compiled "unobserved values" function the reference evaluates per
  * draw (pymc/backends/base.py:184-191, ndarray.py:108; transforms pymc/logprob/transforms.py:880-891, :1026-1045). */
 int b200_model_set_transforms(b200_model* model, const int8_t* kind, const double* lo, const double* hi);
+/* Fixed dense mass matrix for B200_MASS_DENSE runs of ANY model (host matrices [n][n] row-major, copied):
+ *   velocity v = cov . p,  momentum p0 = mp0 . z,  its velocity v0 = mv0 . z   with z ~ N(0, I).
+ * QuadPotentialFull(cov)   (quadpotential.py:680-725): mp0 = L^-T, mv0 = L with L = cholesky(cov, lower)
+ * QuadPotentialFullInv(A)  (quadpotential.py:633-677): cov = A^-1, mp0 = cholesky(A, lower), mv0 = mp0^-T
+ * (the host binding computes the factors; see pymc_b200.engine.CompiledModel.set_dense_mass).  Dense-mass runs advance all
+ * chains in lock step: one model evaluation kernel + one fp64 tensor-core GEMM (Sigma . grad) per leapfrog. */
+int b200_model_set_dense_mass(b200_model* model, const double* cov, const double* mp0, const double* mv0);
 int b200_model_n(const b200_model* model);
 
 /* Replaces: ValueGradFunction._pytensor_function(q) -> (logp, dlogp), batched over C points

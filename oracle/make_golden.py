@@ -259,9 +259,45 @@ def f3_cases():
         print(name + "_adapt_grad", "grad evals", int(out["stat_tree_size"].sum()))
 
 
+def dense_any_cases():
+    """QuadPotentialFull / QuadPotentialFullInv on a model that is NOT a Gaussian (Radon): the dense mass matrix is model-
+    independent in the reference (quadpotential.py:633-725).  Fixed step size, start and diagonal from the radon_fixed golden,
+    plus a rank-5 correlation."""
+    qp = ref_loader.quadpotential()
+    base = dict(np.load(os.path.join(OUT, "radon_fixed.npz")))
+    spec = models.radon()
+    n = spec.n
+    rng = np.random.default_rng(61)
+    var = base["var"][0]
+    U = rng.standard_normal((n, 5)) * 0.3 * np.sqrt(var)[:, None]
+    cov = np.diag(var) + U @ U.T
+    cov = 0.5 * (cov + cov.T)
+    A = np.linalg.inv(cov)
+    A = 0.5 * (A + A.T)
+    eps = float(base["eps"][0]) * 0.8
+    for tag, pot_of in (("full", lambda: qp.QuadPotentialFull(cov)), ("fullinv", lambda: qp.QuadPotentialFullInv(A))):
+        C, draws = 2, 8
+        q0s = [base["q0"][c] for c in range(C)]
+        seeds = [951 + c for c in range(C)]
+        Q, ST, PR = [], [], []
+        for c in range(C):
+            q, sts, pre, step = run_reference_generic(spec, q0s[c], seed=seeds[c], tune=0, draws=draws, potential=pot_of(),
+                                                      adapt=False, step_kwargs={"step_scale": eps * n**0.25})
+            Q.append(q); ST.append(sts); PR.append(pre)
+        out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=0, draws=draws, draws_q=np.array(Q), pre_rng=np.array(PR),
+                   z=np.array([noise(s, draws, n) for s in seeds]), cov=cov, A=A, eps=np.full(C, eps), dense=True, adapt=False)
+        for k in STAT_KEYS:
+            out["stat_" + k] = np.array([[s[k] for s in sts] for sts in ST])
+        np.savez_compressed(os.path.join(OUT, f"radon_dense_{tag}_fixed.npz"), **out)
+        print(f"radon_dense_{tag}_fixed", "grad evals", int(out["stat_tree_size"].sum()), "mean depth", out["stat_depth"].mean())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lockstep":
         lockstep_cases()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dense_any":
+        dense_any_cases()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f3":
         f3_cases()

@@ -169,6 +169,25 @@ class DenseMass:
         pass
 
 
+class DenseInvMass(DenseMass):
+    """QuadPotentialFullInv (quadpotential.py:633-677): A = inverse covariance; v = cho_solve(chol(A), p); p0 = chol(A) z."""
+
+    def __init__(self, A):
+        self.L = sl.cholesky(np.array(A, dtype="d"), lower=True)
+        self.n = len(self.L)
+        self.rng = None
+
+    def velocity(self, p, out=None):
+        vel = sl.cho_solve((self.L, True), p)
+        if out is None:
+            return vel
+        out[:] = vel
+        return out
+
+    def momentum(self, z):
+        return np.dot(self.L, z)
+
+
 # ------------------------------------------------------------------------------------------------
 # step-size adaptation
 # ------------------------------------------------------------------------------------------------

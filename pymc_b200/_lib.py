@@ -228,6 +228,7 @@ SYMBOLS = [
     ("b200_model_n", C.c_int, [C.c_void_p]),
     ("b200_model_set_precision", C.c_int, [C.c_void_p, C.c_int32]),
     ("b200_model_set_transforms", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_model_set_dense_mass", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_logp_dlogp", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     (
         "b200_leapfrog",
@@ -255,7 +256,8 @@ def load() -> C.CDLL:
             raise B200Error(f"{LIB_PATH} is missing: build the CUDA engine first (./build.sh); there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)
         for name, restype, argtypes in SYMBOLS:
-            if name in ("b200_struct_size", "b200_model_set_precision", "b200_model_set_transforms") and not hasattr(lib, name):
+            if name in ("b200_struct_size", "b200_model_set_precision", "b200_model_set_transforms",
+                        "b200_model_set_dense_mass") and not hasattr(lib, name):
                 continue  # an A/B build (B200_LIB=...) older than ABI 0.2.0; tests/test_abi.py requires it of the in-tree library
             fn = getattr(lib, name)
             fn.restype = restype

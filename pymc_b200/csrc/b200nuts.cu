@@ -82,9 +82,10 @@ struct b200_model {
     // lock-step (GEMM-shaped) models; every matrix is row-major with rows `ld` doubles apart (n rounded up to 4, zero pad)
     long long ld = 0;
     const double* prec = nullptr;   // MVGAUSS: precision P [n][ld]
-    const double* cov = nullptr;    // MVGAUSS: covariance Sigma [n][ld] (dense mass matrix)
-    const double* linvT = nullptr;  // MVGAUSS: L^-T [n][ld]   (p0 = L^-T z)
-    const double* chol = nullptr;   // MVGAUSS: L    [n][ld]   (v0 = Sigma p0 = L z)
+    // dense mass matrix of ANY model (b200_model_set_dense_mass; MVGAUSS sets it from its own covariance at create)
+    const double* cov = nullptr;    // velocity:  v = cov p            (QuadPotentialFull: Sigma; FullInv: A^-1)   [n][ld]
+    const double* linvT = nullptr;  // momentum:  p0 = linvT z         (Full: L^-T, L = chol(Sigma); FullInv: chol(A))
+    const double* chol = nullptr;   // its velocity: v0 = chol z       (Full: L;    FullInv: chol(A)^-T)
     double logp_const = 0.0;
     const double* X = nullptr;      // LOGISTIC: design matrix [Npad][KP] row-major, zero padded (KP = 8, 32 or 128)
     const uint8_t* y8 = nullptr;    // LOGISTIC: y[N]
@@ -117,6 +118,7 @@ struct b200_model {
 };
 
 static bool is_lockstep_kind(int kind);
+template <class F> static int dispatch(const b200_model* m, F&& f);
 static int lockstep_logp(b200_model* m, const double* q_dev, int C, double* logp_dev, double* grad_dev, cudaStream_t st);
 
 template <class T>
@@ -469,6 +471,19 @@ extern "C" int b200_model_create(const b200_model_desc* desc, b200_model** out) 
 
 extern "C" void b200_model_destroy(b200_model* m) { delete m; }
 
+extern "C" int b200_model_set_dense_mass(b200_model* m, const double* cov, const double* mp0, const double* mv0) {
+    if (!m || !cov || !mp0 || !mv0) return fail("b200_model_set_dense_mass: null argument");
+    if (m->cov) return fail("b200_model_set_dense_mass: this handle already has a dense mass matrix");
+    CU(cudaSetDevice(m->device));
+    const size_t n = (size_t)m->n;
+    if (!m->ld) m->ld = (long long)((n + 3) & ~(size_t)3);
+    const size_t ld = (size_t)m->ld;
+    if (upload_padded(m, cov, n, n, n, ld, &m->cov) || upload_padded(m, mp0, n, n, n, ld, &m->linvT) ||
+        upload_padded(m, mv0, n, n, n, ld, &m->chol))
+        return -1;
+    return 0;
+}
+
 extern "C" int b200_model_set_transforms(b200_model* m, const int8_t* kind, const double* lo, const double* hi) {
     if (!m || !kind || !lo || !hi) return fail("b200_model_set_transforms: null argument");
     for (int i = 0; i < m->n; ++i) {
@@ -637,6 +652,7 @@ static int env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 struct LogpLaunch {
     const b200_model* m; int C; const double* q; double* logp; double* grad; cudaStream_t st;
+    long long ldq = 0, ldg = 0;  // row strides (0: contiguous rows of n)
     template <class Model, int NPL, int W>
     int operator()(const typename Model::Params& MP) const {
         const int wpb = (W == 1) ? 8 : 1;  // chains per CTA
@@ -647,7 +663,7 @@ struct LogpLaunch {
         const int blocks = std::max(1, std::min((C + wpb - 1) / wpb, 148 * 8));
         typename Model::Params MPl;
         if (launch_params<Model>(m, MP, (long long)blocks * wpb, &MPl)) return -1;
-        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MPl, m->n, C, q, logp, grad);
+        kern<<<blocks, (W == 1) ? wpb * 32 : 32 * W, smem, st>>>(MPl, m->n, C, q, logp, grad, ldq ? ldq : m->n, ldg ? ldg : m->n);
         CU(cudaGetLastError());
         return 0;
     }
@@ -856,6 +872,12 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
                       int* launches) {
     const int n = m->n;
     const long long ld = m->ld;
+    if (!is_lockstep_kind(m->kind)) {
+        // any other model under a dense mass matrix: its own fused logp+grad device function, one team per requested point
+        LogpLaunch L{m, C, Q, logp, G, st, ld, ld};
+        if (launches) *launches += 1;
+        return dispatch(m, L);
+    }
     if (m->kind == B200_MODEL_MVGAUSS) {
         // grad = -P q  (MvNormal.logp multivariate.py:275-295; P symmetric)
         if (launches) *launches += 1;
@@ -1057,9 +1079,12 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     if (cfg->max_treedepth < 1 || cfg->max_treedepth > kMaxLevels || cfg->early_max_treedepth < 1 ||
         cfg->early_max_treedepth > cfg->max_treedepth)
         return fail("b200_nuts_run: treedepth must satisfy 1 <= early <= max <= %d", kMaxLevels);
-    const bool lockstep = is_lockstep_kind(m->kind);
+    // GEMM-shaped models always advance in lock step; so does any model under a dense mass matrix (v = Sigma p is a GEMM
+    // over all chains on the fp64 tensor path instead of n^2 per chain per leapfrog inside a warp)
+    const bool lockstep = is_lockstep_kind(m->kind) || cfg->mass_kind == B200_MASS_DENSE;
     if (cfg->mass_kind == B200_MASS_DENSE) {
-        if (m->kind != B200_MODEL_MVGAUSS) return fail("b200_nuts_run: the dense mass matrix is the model's covariance (MVGAUSS only)");
+        if (!m->cov) return fail("b200_nuts_run: mass_kind DENSE needs b200_model_set_dense_mass first");
+        if (m->kind == B200_MODEL_LOGISTIC) return fail("b200_nuts_run: dense mass for the logistic GLM is not wired (use a diagonal mass)");
     } else if (cfg->mass_kind == B200_MASS_DIAG_ADAPT_GRAD) {
         if (lockstep) return fail("b200_nuts_run: DIAG_ADAPT_GRAD is implemented by the persistent engine only");
         if (!(cfg->mass_alpha > 0 && cfg->mass_alpha < 1)) return fail("b200_nuts_run: mass_alpha must be in (0, 1)");

@@ -810,7 +810,7 @@ template <class Model, int NPL, int W>
 __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Model::Params M, int n, int C,
                                                              const double* __restrict__ q,
                                                              double* __restrict__ logp_out,
-                                                             double* __restrict__ grad_out) {
+                                                             double* __restrict__ grad_out, long long ldq, long long ldg) {
     constexpr int TS = 32 * W;
     constexpr int NP = TS * NPL;
     extern __shared__ __align__(16) char smem_raw[];
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Mode
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + TS * k;
-            q_s[i] = (i < n) ? q[(long long)c * n + i] : 0.0;
+            q_s[i] = (i < n) ? q[(long long)c * ldq + i] : 0.0;
             g_s[i] = 0.0;
         }
         team_sync<W>();
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(256) logp_grad_warp_kernel(const typename Mode
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int i = lane + TS * k;
-            if (i < n) grad_out[(long long)c * n + i] = g_s[i];
+            if (i < n) grad_out[(long long)c * ldg + i] = g_s[i];
         }
         if (lane == 0) logp_out[c] = lp;
         team_sync<W>();

@@ -120,6 +120,30 @@ class CompiledModel:
         if self.supports_constrain:
             _lib.check(self._lib.b200_model_set_transforms(self._h, kind.ctypes.data, lo.ctypes.data, hi.ctypes.data))
 
+    def set_dense_mass(self, cov=None, *, inverse=None) -> None:
+        """Fixed dense mass matrix for ``nuts_run(mass="dense")``: ``cov`` -> QuadPotentialFull(cov) (quadpotential.py:680-725),
+        ``inverse=A`` -> QuadPotentialFullInv(A) (:633-677).  The Cholesky factors are computed here (SciPy)."""
+        import scipy.linalg as sl
+
+        n = self.n
+        if (cov is None) == (inverse is None):
+            raise ValueError("pass exactly one of cov= or inverse=")
+        eye = np.eye(n)
+        if cov is not None:
+            S = np.ascontiguousarray(cov, dtype=np.float64).reshape(n, n)
+            L = sl.cholesky(S, lower=True)
+            mp0 = sl.solve_triangular(L, eye, lower=True).T.copy()  # L^-T: p0 = solve_triangular(L.T, z)
+            mv0 = L
+        else:
+            A = np.ascontiguousarray(inverse, dtype=np.float64).reshape(n, n)
+            LA = sl.cholesky(A, lower=True)
+            S = sl.cho_solve((LA, True), eye)                          # velocity = cho_solve(L, x) = A^-1 x
+            S = 0.5 * (S + S.T)
+            mp0 = LA                                                   # random() = L . normal
+            mv0 = sl.solve_triangular(LA, eye, lower=True).T.copy()    # v0 = A^-1 L z = L^-T z
+        S, mp0, mv0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (S, mp0, mv0))
+        _lib.check(self._lib.b200_model_set_dense_mass(self._h, S.ctypes.data, mp0.ctypes.data, mv0.ctypes.data))
+
     def set_precision(self, mode: str) -> None:
         """"fp64" (parity mode, default) or "tc_fp16x2": the dense contractions of the logistic GLM on the tcgen05 tensor
         cores with split-fp16 operands (performance mode; gradient ~1e-7 relative, see include/b200nuts.h)."""

@@ -342,6 +342,12 @@ int b200_nuts_run(b200_model* model, const b200_nuts_cfg* cfg, const double* q0,
                   const b200_stats* stats, const b200_chain_summary* summary, int32_t mem,
                   void* stream);
 
+/* Pointwise log-likelihood of likelihood factor `lik` of an IR model for D unconstrained draws:
+ * out[d][i] = log p(y_i | draws[d]).  Replaces pm.compute_log_likelihood's per-draw compiled function
+ * (pymc/stats/log_density.py:31-77, :129-195): the `log_likelihood` group of the InferenceData. */
+int b200_pointwise_loglik(b200_model* model, int32_t lik, const double* draws /*[D][n]*/, int64_t D,
+                          double* out /*[D][N]*/, int32_t mem, void* stream);
+
 /* Device time (ms, CUDA events on the launching stream) and launch count of the kernels of the
  * most recent b200_nuts_run / b200_logp_dlogp / b200_leapfrog call on this thread. */
 int b200_last_kernel_ms(double* ms, int32_t* launches);

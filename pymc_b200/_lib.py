@@ -240,6 +240,7 @@ SYMBOLS = [
         C.c_int,
         [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 7 + [C.POINTER(Stats), C.POINTER(ChainSummary), C.c_int32, C.c_void_p],
     ),
+    ("b200_pointwise_loglik", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     ("b200_last_kernel_ms", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     ("b200_measure_fp64_tflops", C.c_int, [C.POINTER(C.c_double)]),
     ("b200_measure_dmma_tflops", C.c_int, [C.POINTER(C.c_double)]),
@@ -257,7 +258,7 @@ def load() -> C.CDLL:
         lib = C.CDLL(LIB_PATH)
         for name, restype, argtypes in SYMBOLS:
             if name in ("b200_struct_size", "b200_model_set_precision", "b200_model_set_transforms",
-                        "b200_model_set_dense_mass") and not hasattr(lib, name):
+                        "b200_model_set_dense_mass", "b200_pointwise_loglik") and not hasattr(lib, name):
                 continue  # an A/B build (B200_LIB=...) older than ABI 0.2.0; tests/test_abi.py requires it of the in-tree library
             fn = getattr(lib, name)
             fn.restype = restype

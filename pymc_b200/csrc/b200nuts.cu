@@ -16,6 +16,7 @@
 #include "dense.cuh"
 #include "ir_model.cuh"
 #include "logistic_tc.cuh"
+#include "gemm_tc.cuh"
 #include "lockstep.cuh"
 #include "models.cuh"
 #include "nuts_warp.cuh"
@@ -97,6 +98,13 @@ struct b200_model {
     const __half* Xl = nullptr;
     long long tc_slabs = 0;
     CUtensorMap map_hi{}, map_lo{};
+    // dense Gaussian, tensor-core performance mode (csrc/gemm_tc.cuh): fp16 pieces of the n x n matrices (B operands) and the
+    // per-call pieces of the chains' vectors (A operand)
+    struct TcMat { const double* src = nullptr; const __half* hi = nullptr; const __half* lo = nullptr; CUtensorMap map_hi{}, map_lo{}; };
+    TcMat tc_mats[4];
+    long long tc_kpad = 0, tc_npad = 0;
+    __half* tc_a_hi = nullptr; __half* tc_a_lo = nullptr;   // [tc_a_rows][tc_kpad]
+    long long tc_a_rows = 0;
     // per-chain tree scratch of the persistent kernel, kept between runs (cudaMalloc/cudaFree of 100+ MB per call costs
     // tens of milliseconds of host time on the end-to-end path)
     void* scratch = nullptr;
@@ -111,6 +119,8 @@ struct b200_model {
         return e;
     }
     ~b200_model() {
+        if (tc_a_hi) cudaFree(tc_a_hi);
+        if (tc_a_lo) cudaFree(tc_a_lo);
         if (ir_scratch) cudaFree(ir_scratch);
         if (scratch) cudaFree(scratch);
         for (void* p : owned) cudaFree(p);
@@ -766,9 +776,16 @@ static int launch_gemm(cudaStream_t st, const double* Q, long long ldq, int C, c
 
 // D[C][Nout] = alpha * Q[C][K] . M[Nout][K]^T.  Tile shape picked per call: chains per CTA from C, outputs per CTA
 // (8 NB) so that the tile count fills whole waves of 148 SMs.
-static int gemm_nt(cudaStream_t st, const double* Q, long long ldq, int C, const double* M, long long ldm, int Nout, int K,
+static int gemm_nt_tc(b200_model* m, cudaStream_t st, const double* Q, long long ldq, int C, const b200_model::TcMat& T, int Nout,
+                      double alpha, double* D, long long ldd);
+
+static int gemm_nt(b200_model* m, cudaStream_t st, const double* Q, long long ldq, int C, const double* M, long long ldm, int Nout, int K,
                    double alpha, double* D, long long ldd) {
     if (C <= 0 || Nout <= 0) return 0;
+    if (m && m->precision == B200_PRECISION_TC_FP16X2) {
+        for (const b200_model::TcMat& T : m->tc_mats)
+            if (T.src == M && T.hi) return gemm_nt_tc(m, st, Q, ldq, C, T, Nout, alpha, D, ldd);
+    }
     const int wm = C > 64 ? 8 : (C > 32 ? 4 : 2);
     const int cb = (C + 16 * wm - 1) / (16 * wm);
     int best_nb = 9;
@@ -803,7 +820,8 @@ typedef CUresult (*b200_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_x_map(CUtensorMap* map, const __half* base, long long rows) {
+// K-major fp16 matrix [rows][kpad] -> tensor map with boxes of 64 k (one 128-byte swizzle row) x box_rows rows
+static int make_tc_map(CUtensorMap* map, const __half* base, long long rows, long long kpad, int box_rows) {
     static b200_encode_tiled_fn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -812,14 +830,70 @@ static int make_x_map(CUtensorMap* map, const __half* base, long long rows) {
         if (!fn || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available in this driver");
         encode = reinterpret_cast<b200_encode_tiled_fn>(fn);
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)kTcK, (cuuint64_t)rows};       // innermost first: features, rows
-    const cuuint64_t strides[1] = {(cuuint64_t)kTcK * sizeof(__half)};     // row pitch in bytes
-    const cuuint32_t box[2] = {64, (cuuint32_t)kTcRows};                   // 64 features (128 B) x 128 rows
+    const cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};         // innermost first
+    const cuuint64_t strides[1] = {(cuuint64_t)kpad * sizeof(__half)};       // row pitch in bytes
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+static int make_x_map(CUtensorMap* map, const __half* base, long long rows) { return make_tc_map(map, base, rows, kTcK, kTcRows); }
+
+// dense Gaussian: split the four n x n matrices once
+static int prepare_mvgauss_tc(b200_model* m) {
+    if (m->tc_mats[0].hi) return 0;
+    const long long n = m->n;
+    m->tc_kpad = (n + kGtKB - 1) / kGtKB * kGtKB;
+    m->tc_npad = (n + kGtN - 1) / kGtN * kGtN;
+    const double* src[4] = {m->prec, m->cov, m->linvT, m->chol};
+    for (int i = 0; i < 4; ++i) {
+        void *h = nullptr, *l = nullptr;
+        const size_t bytes = (size_t)m->tc_npad * m->tc_kpad * sizeof(__half);
+        CU(cudaMalloc(&h, bytes));
+        m->owned.push_back(h);
+        CU(cudaMalloc(&l, bytes));
+        m->owned.push_back(l);
+        const long long total = m->tc_npad * m->tc_kpad;
+        gemm_tc_split_kernel<<<(unsigned)((total + 255) / 256), 256>>>(src[i], n, n, m->ld, (__half*)h, (__half*)l, m->tc_npad, m->tc_kpad);
+        CU(cudaGetLastError());
+        b200_model::TcMat& T = m->tc_mats[i];
+        T.src = src[i]; T.hi = (const __half*)h; T.lo = (const __half*)l;
+        if (make_tc_map(&T.map_hi, T.hi, m->tc_npad, m->tc_kpad, kGtN) || make_tc_map(&T.map_lo, T.lo, m->tc_npad, m->tc_kpad, kGtN)) return -1;
+    }
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+// D[C][Nout] = alpha Q . M^T on the tensor cores; M must be one of the model's pre-split matrices
+static int gemm_nt_tc(b200_model* m, cudaStream_t st, const double* Q, long long ldq, int C, const b200_model::TcMat& T, int Nout,
+                      double alpha, double* D, long long ldd) {
+    const long long rows_pad = ((long long)C + kGtM - 1) / kGtM * kGtM;
+    if (rows_pad > m->tc_a_rows) {
+        if (m->tc_a_hi) cudaFree(m->tc_a_hi);
+        if (m->tc_a_lo) cudaFree(m->tc_a_lo);
+        m->tc_a_hi = m->tc_a_lo = nullptr;
+        m->tc_a_rows = 0;
+        CU(cudaMalloc((void**)&m->tc_a_hi, (size_t)rows_pad * m->tc_kpad * sizeof(__half)));
+        CU(cudaMalloc((void**)&m->tc_a_lo, (size_t)rows_pad * m->tc_kpad * sizeof(__half)));
+        m->tc_a_rows = rows_pad;
+    }
+    const long long total = rows_pad * m->tc_kpad;
+    gemm_tc_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, C, m->n, ldq, m->tc_a_hi, m->tc_a_lo, rows_pad, m->tc_kpad);
+    CU(cudaGetLastError());
+    CUtensorMap a_hi, a_lo;
+    if (make_tc_map(&a_hi, m->tc_a_hi, rows_pad, m->tc_kpad, kGtM) || make_tc_map(&a_lo, m->tc_a_lo, rows_pad, m->tc_kpad, kGtM)) return -1;
+    GemmTcArgs G{};
+    G.C = C; G.Nout = Nout; G.n_kblocks = (int)(m->tc_kpad / kGtKB); G.alpha = alpha; G.D = D; G.ldd = ldd;
+    G.n_tiles_n = (int)(m->tc_npad / kGtN);
+    G.n_tiles = G.n_tiles_n * (int)(rows_pad / kGtM);
+    auto kern = gemm_tc_kernel;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmemBytes));
+    const int grid = std::min(G.n_tiles, 148);
+    kern<<<grid, kGtThreads, kGtSmemBytes, st>>>(a_hi, a_lo, T.map_hi, T.map_lo, G);
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -846,9 +920,10 @@ extern "C" int b200_model_set_precision(b200_model* m, int32_t mode) {
     if (!m) return fail("b200_model_set_precision: null model");
     if (mode != B200_PRECISION_FP64 && mode != B200_PRECISION_TC_FP16X2) return fail("b200_model_set_precision: unknown mode %d", mode);
     if (mode == B200_PRECISION_TC_FP16X2) {
-        if (m->kind != B200_MODEL_LOGISTIC) return fail("tensor-core mode is implemented for the logistic GLM (dense design-matrix contraction) only");
+        if (m->kind != B200_MODEL_LOGISTIC && m->kind != B200_MODEL_MVGAUSS)
+            return fail("tensor-core mode is implemented for the dense contractions: the logistic GLM and the dense Gaussian");
         CU(cudaSetDevice(m->device));
-        if (prepare_logistic_tc(m)) return -1;
+        if (m->kind == B200_MODEL_LOGISTIC ? prepare_logistic_tc(m) : prepare_mvgauss_tc(m)) return -1;
     }
     m->precision = mode;
     return 0;
@@ -881,7 +956,7 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
     if (m->kind == B200_MODEL_MVGAUSS) {
         // grad = -P q  (MvNormal.logp multivariate.py:275-295; P symmetric)
         if (launches) *launches += 1;
-        return gemm_nt(st, Q, ld, C, m->prec, ld, n, (int)ld, -1.0, G, ld);
+        return gemm_nt(m, st, Q, ld, C, m->prec, ld, n, (int)ld, -1.0, G, ld);
     }
     // logistic: one fused pass over X, then the fixed-order reduction of the row-CTA partials
     const int cb = (C + kLogiChains - 1) / kLogiChains;
@@ -977,13 +1052,13 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
         if (batch_eval(m, C, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
         if (dense) {
             // w = Sigma g for every requested point (QuadPotentialFull.velocity, quadpotential.py:705-707)
-            if (gemm_nt(st, P.Greq, ld, C, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
+            if (gemm_nt(m, st, P.Greq, ld, C, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
             ++launches;
             if (n_mom > 0) {
                 ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb.as<double>());
                 // p0 = L^-T z (solve_triangular(chol.T, z), quadpotential.py:710-713);  v0 = Sigma p0 = L z
-                if (gemm_nt(st, Zb.as<double>(), ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b.as<double>(), ld)) return -1;
-                if (gemm_nt(st, Zb.as<double>(), ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b.as<double>(), ld)) return -1;
+                if (gemm_nt(m, st, Zb.as<double>(), ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b.as<double>(), ld)) return -1;
+                if (gemm_nt(m, st, Zb.as<double>(), ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b.as<double>(), ld)) return -1;
                 ls_scatter_mom_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, P0b.as<double>(), V0b.as<double>());
                 CU(cudaGetLastError());
                 launches += 4;
@@ -1225,6 +1300,33 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     for (auto& s : st_arr) if (stage_out(s, st)) return -1;
     for (auto& s : sm_arr) if (stage_out(s, st)) return -1;
     for (auto& s : st_state) if (stage_out(s, st)) return -1;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int b200_pointwise_loglik(b200_model* m, int32_t lik, const double* draws, int64_t D, double* out, int32_t mem,
+                                     void* stream) {
+    if (!m || !draws || !out) return fail("b200_pointwise_loglik: null argument");
+    if (m->kind != B200_MODEL_IR) return fail("b200_pointwise_loglik: implemented for IR models (b200_ir likelihood factors)");
+    if (lik < 0 || lik >= m->ir.n_liks) return fail("b200_pointwise_loglik: likelihood index %d out of range", lik);
+    if (D <= 0) return 0;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the IR tables live on the device: read the number of observations of this factor back
+    IrLikD L;
+    CU(cudaMemcpy(&L, m->ir.liks + lik, sizeof L, cudaMemcpyDeviceToHost));
+    Staged s_in, s_out;
+    if (stage_in(s_in, draws, (size_t)D * m->n * sizeof(double), mem, true, false, st) ||
+        stage_in(s_out, out, (size_t)D * (size_t)L.N * sizeof(double), mem, false, true, st))
+        return -1;
+    const int wpb = 8;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((D + wpb - 1) / wpb, 148 * 8));
+    CU(m->ensure_ir_scratch((long long)blocks * wpb));
+    Timer t(st);
+    ir_pointwise_kernel<<<blocks, wpb * 32, 0, st>>>(m->ir, lik, D, (const double*)s_in.ptr(), (double*)s_out.ptr());
+    CU(cudaGetLastError());
+    t.stop(1);
+    if (stage_out(s_out, st)) return -1;
     CU(cudaStreamSynchronize(st));
     return 0;
 }

@@ -295,4 +295,65 @@ struct IrModel {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Pointwise log-likelihood of one likelihood factor for a batch of (unconstrained) draws: out[d][i] = log p(y_i | draw d).
+// What pm.compute_log_likelihood evaluates per draw through a compiled function (pymc/stats/log_density.py:31-77,
+// :129-195) -- the `log_likelihood` group LOO / WAIC need.  One warp per draw; the constrained values go through the
+// team scratch slice like in eval().  Elementwise constants (log 2pi, lgamma) are included, unlike in eval() where they are
+// folded into one constant per factor.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ir_pointwise_kernel(const IrModel::Params P, int lik, long long D,
+                                                           const double* __restrict__ draws /*[D][n]*/,
+                                                           double* __restrict__ out /*[D][N]*/) {
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    double* x = P.scratch + (long long)slot * P.stride;
+    const IrLikD L = P.liks[lik];
+    const int N = (int)L.N, n = P.n;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long d = slot; d < D; d += stride) {
+        const double* q = draws + d * n;
+        for (int v = 0; v < P.n_vars; ++v) {
+            const IrVarD V = P.vars[v];
+            for (int j = lane; j < V.size; j += 32) {
+                const double z = q[V.offset + j];
+                x[V.offset + j] = V.transform == IRT_LOG ? exp(z) : (V.transform == IRT_INTERVAL ? V.lo + (V.hi - V.lo) * sigmoid(z) : z);
+            }
+        }
+        __syncwarp();
+        const double sg_s = (L.sigma_kind == IRS_REF) ? x[L.sigma.ref] : L.sigma.value;
+        for (int i = lane; i < N; i += 32) {
+            double eta = 0.0;
+            for (int t = 0; t < L.n_terms; ++t) {
+                const IrTermD& Tm = P.terms[L.term0 + t];
+                double pr = Tm.coef ? Tm.coef[i] : 1.0;
+                for (int f = 0; f < Tm.n_factors; ++f) {
+                    const IrFactorD& Fc = Tm.f[f];
+                    pr *= x[Fc.offset + (Fc.idx ? Fc.idx[i] : (Fc.size == 1 ? 0 : i))];
+                }
+                eta += pr;
+            }
+            const double yi = L.y[i];
+            double lp = 0.0;
+            switch (L.dist) {
+                case IRL_NORMAL: {
+                    const double sg = (L.sigma_kind == IRS_OBS) ? L.sigma_obs[i] : sg_s, z = (yi - eta) / sg;
+                    lp = -0.5 * z * z - log(sg) - B200_HALF_LOG_2PI;
+                } break;
+                case IRL_BERNOULLI_LOGIT: lp = yi * eta - softplus(eta); break;
+                case IRL_POISSON_LOG: lp = yi * eta - exp(eta) - lgamma(yi + 1.0); break;
+                case IRL_STUDENTT: {
+                    const double sg = (L.sigma_kind == IRS_OBS) ? L.sigma_obs[i] : sg_s, z = (yi - eta) / sg;
+                    lp = lgamma(0.5 * (L.nu + 1.0)) - lgamma(0.5 * L.nu) - 0.5 * log(L.nu * 3.14159265358979323846) - log(sg) -
+                         0.5 * (L.nu + 1.0) * log1p(z * z / L.nu);
+                } break;
+                case IRL_NORMAL_LOGVAR: lp = -0.5 * yi * yi * exp(-eta) - 0.5 * eta - B200_HALF_LOG_2PI; break;
+                default: break;
+            }
+            out[d * N + i] = lp;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace b200

@@ -5,10 +5,10 @@
 // tcgen05 has no fp64 kind, so every fp64 operand is split into two fp16 pieces, v = hi + lo with hi = fp16(v) and
 // lo = fp16(v - hi) (22 significant bits; absolute floor 2^-25 where lo is subnormal), and a product is evaluated as
 // hi*hi + hi*lo + lo*hi in three kind::f16 MMAs with fp32 accumulation (the lo*lo term is below 2^-22 relative).
-// fp32 accumulators only ever cover a bounded number of rows: X beta sums K = 128 terms, and the gradient accumulator in
-// TMEM is drained into fp64 every kTcDrain slabs (2048 rows), so the fp32 rounding of a long sum never builds up.
-// Measured accuracy against the fp64 path (tests/test_gpu_tc.py; profiles/r2_tc_accuracy.json): gradient ~1e-7 relative to
-// its largest entry, logp ~1e-9 relative.  The fp64 DMMA kernel stays the parity mode.
+// fp32 accumulators only ever cover one slab: X beta sums K = 128 terms, and the gradient accumulator in TMEM is drained
+// into fp64 after every 128-row slab, so neither fp32 rounding nor the tensor cores' one-sided accumulate rounding builds up.
+// Accuracy against the fp64 path is measured by tests/test_gpu_tc.py and reported in profiles/ (parity report).  The fp64
+// DMMA kernel stays the parity mode.
 //
 // One CTA = 128 chains x a strided set of 128-row slabs of X.  Per slab (FlashAttention-shaped, P kept in TMEM):
 //   TMA   : X_hi, X_lo slab [128 rows][128 features] fp16 -> smem (SWIZZLE_128B, two 64-column boxes each), 2 stages
@@ -16,8 +16,9 @@
 //   epilog: thread c (TMEM lane c) reads its 128 eta values (tcgen05.ld), computes r = y - sigmoid(eta) and the
 //           log-likelihood terms in fp32, splits r into fp16 pieces and writes them back to TMEM (tcgen05.st)
 //   GEMM 2: D2[c][k] += sum_i r[c][i] X[i][k]        A = r pieces (TMEM), B = the SAME X bytes read MN-major
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (one TMEM
-// subpartition each).  D1 is double-buffered so GEMM 1 of slab s+1 runs under the epilogue of slab s.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (two per TMEM
+// subpartition, 64 rows of the slab each: the elementwise sigmoid / softplus work is what bounds the kernel, so it gets two
+// warps per scheduler).  D1 is double-buffered so GEMM 1 of slab s+1 runs under the epilogue of slab s.
 // TMEM columns (512): D1[0] 0..127, D1[1] 128..255, D2 256..383, r_hi 384..447, r_lo 448..511.
 #pragma once
 #include <cuda.h>
@@ -31,8 +32,8 @@ constexpr int kTcRows = 128;      // rows of X per slab (N of GEMM 1, K of GEMM 
 constexpr int kTcChains = 128;    // chains per CTA (M of both GEMMs = TMEM lanes)
 constexpr int kTcK = 128;         // features (padded)
 constexpr int kTcStages = 2;      // X slab stages in shared memory
-constexpr int kTcDrain = 16;      // slabs between drains of the fp32 gradient accumulator into fp64
-constexpr int kTcThreads = 192;   // 6 warps
+constexpr int kTcThreads = 320;   // 10 warps: TMA producer, MMA issuer, 8 epilogue
+constexpr int kTcEpiThreads = 256;
 constexpr uint32_t kTcBlockBytes = kTcRows * 64 * 2;          // one [128 rows][64 cols] fp16 box = 16 KB
 constexpr uint32_t kTcPieceBytes = 2 * kTcBlockBytes;         // one piece of a [128][128] tile = 32 KB
 constexpr uint32_t kTcStageBytes = 2 * kTcPieceBytes;         // X_hi + X_lo = 64 KB
@@ -144,6 +145,11 @@ struct LogisticTcArgs {
     int Cpad;
 };
 
+// Accumulation order and drain period are dictated by the tensor cores' fp32 accumulate, which rounds toward zero: every
+// tcgen05.mma into an accumulator of magnitude |D| loses ~2^-25 |D| one-sidedly (measured, round 2 call 3: 24 accumulate
+// steps per slab -> 8e-7, 384 steps -> 7.9e-6 relative).  So (i) the small correction products hi*lo and lo*hi are issued
+// FIRST, while the accumulator is still tiny, and hi*hi last: 8 full-magnitude steps per GEMM instead of 24; (ii) the
+// gradient accumulator is drained into fp64 after EVERY slab.
 __global__ void __launch_bounds__(kTcThreads, 1)
     logistic_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const LogisticTcArgs A) {
     extern __shared__ char tc_smem_raw[];
@@ -156,10 +162,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint64_t* eta_full = bars + 4;    // [2] MMA (GEMM 1 done) -> epilogue
     uint64_t* eta_empty = bars + 6;   // [2] epilogue (D1 read) -> MMA
     uint64_t* r_full = bars + 8;      // epilogue (r written) -> MMA
-    uint64_t* r_empty = bars + 9;     // MMA (GEMM 2 done) -> epilogue
-    uint64_t* g_full = bars + 10;     // MMA (drain point reached) -> epilogue
-    uint64_t* g_empty = bars + 11;    // epilogue (D2 drained) -> MMA
+    uint64_t* g_full = bars + 9;      // MMA (GEMM 2 of a slab done: D2 complete, r and the X stage free) -> epilogue
+    uint64_t* g_empty = bars + 10;    // epilogue (D2 drained) -> MMA
     __shared__ uint32_t tmem_base_s;
+    __shared__ double lp_half_s[kTcChains];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c_base = blockIdx.y * kTcChains;
@@ -171,12 +177,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(&x_full[i], 1);
             mbar_init(&x_empty[i], 1);
             mbar_init(&eta_full[i], 1);
-            mbar_init(&eta_empty[i], 128);
+            mbar_init(&eta_empty[i], kTcEpiThreads);
         }
-        mbar_init(r_full, 128);
-        mbar_init(r_empty, 1);
+        mbar_init(r_full, kTcEpiThreads);
         mbar_init(g_full, 1);
-        mbar_init(g_empty, 128);
+        mbar_init(g_empty, kTcEpiThreads);
     }
     if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM by construction: 193 KB of shared memory)
         const uint32_t ncols = 512;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ===== MMA issuer (one lane) =====
         if (lane == 0) {
             const uint32_t beta_a = smem_u32(beta_s);
-            auto gemm1 = [&](long long s) {  // D1[s & 1] = beta . X^T   (3 products x 8 k-steps)
+            auto gemm1 = [&](long long s) {  // D1[s & 1] = beta . X^T   (3 products x 8 k-steps, small products first)
                 const int st = (int)(s % kTcStages), b = (int)(s & 1);
                 tc_mbar_wait(&x_full[st], (uint32_t)((s / kTcStages) & 1));
                 if (s >= 2) tc_mbar_wait(&eta_empty[b], (uint32_t)(((s >> 1) - 1) & 1));
@@ -228,9 +233,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t xa = smem_u32(x_s + st * kTcStageBytes);
                 uint32_t acc = 0;
 #pragma unroll
-                for (int prod = 0; prod < 3; ++prod) {  // hi*hi, hi*lo, lo*hi
-                    const uint32_t a0 = beta_a + (prod == 2 ? kTcPieceBytes : 0);
-                    const uint32_t b0 = xa + (prod == 1 ? kTcPieceBytes : 0);
+                for (int prod = 0; prod < 3; ++prod) {  // hi*lo, lo*hi, hi*hi
+                    const uint32_t a0 = beta_a + (prod == 1 ? kTcPieceBytes : 0);
+                    const uint32_t b0 = xa + (prod == 0 ? kTcPieceBytes : 0);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t o = (uint32_t)((ks >> 2) * kTcBlockBytes + (ks & 3) * 32);
@@ -243,18 +248,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (my_slabs > 0) gemm1(0);
             for (long long s = 0; s < my_slabs; ++s) {
                 if (s + 1 < my_slabs) gemm1(s + 1);
-                // GEMM 2 of slab s: D2 += r . X   (A = r pieces in TMEM, B = X pieces read MN-major)
+                // GEMM 2 of slab s: D2 = r . X   (A = r pieces in TMEM, B = X pieces read MN-major); D2 was drained
                 tc_mbar_wait(r_full, (uint32_t)(s & 1));
-                const bool first = (s % kTcDrain) == 0;
-                if (first && s > 0) tc_mbar_wait(g_empty, (uint32_t)(((s / kTcDrain) - 1) & 1));
+                if (s > 0) tc_mbar_wait(g_empty, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 const int st = (int)(s % kTcStages);
                 const uint32_t xa = smem_u32(x_s + st * kTcStageBytes);
-                uint32_t acc = first ? 0u : 1u;
+                uint32_t acc = 0;
 #pragma unroll
-                for (int prod = 0; prod < 3; ++prod) {  // r_hi X_hi, r_hi X_lo, r_lo X_hi
-                    const uint32_t ta = (prod == 2) ? tRl : tRh;
-                    const uint32_t b0 = xa + (prod == 1 ? kTcPieceBytes : 0);
+                for (int prod = 0; prod < 3; ++prod) {  // r_hi X_lo, r_lo X_hi, r_hi X_hi
+                    const uint32_t ta = (prod == 1) ? tRl : tRh;
+                    const uint32_t b0 = xa + (prod == 0 ? kTcPieceBytes : 0);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {  // 16 rows of the slab per step: 2 KB of each 64-column block
                         tc_mma_ts(tD2, ta + ks * 8, tc_desc(b0 + ks * 2048, kTcBlockBytes, 1024), kTcIdescBmn, acc);
@@ -262,27 +266,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                 }
                 tc_commit(&x_empty[st]);
-                tc_commit(r_empty);
-                if ((s + 1) % kTcDrain == 0 || s + 1 == my_slabs) tc_commit(g_full);
+                tc_commit(g_full);
             }
         }
     } else {
-        // ===== epilogue: thread = chain (TMEM lane), warp w owns subpartition w % 4 =====
-        const int sub = warp & 3;
+        // ===== epilogue: 8 warps; TMEM lane = chain (subpartition = warp % 4), the two warps of a subpartition split the
+        //       slab's 128 rows (and the 128 gradient columns of a drain) in halves =====
+        const int sub = warp & 3, half = (warp - 2) >> 2;
         const int c = sub * 32 + lane;                       // chain inside the CTA = TMEM lane
         const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
         double lp = 0.0;
-        const long long gp_off = ((long long)blockIdx.x * A.Cpad + c_base + c) * kTcK;
+        double* gp = A.Gpart + ((long long)blockIdx.x * A.Cpad + c_base + c) * kTcK + half * 64;
         bool g_first = true;
-        long long n_drained = 0;
-        auto drain = [&]() {  // fp32 gradient accumulator -> this CTA's fp64 partial (global, L2 resident)
-            tc_mbar_wait(g_full, (uint32_t)(n_drained & 1));
+        auto drain = [&](long long s_done) {  // fp32 gradient of slab s_done -> this CTA's fp64 partial (global, L2 resident)
+            tc_mbar_wait(g_full, (uint32_t)(s_done & 1));
             tc_fence_after();
-            double* gp = A.Gpart + gp_off;
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 uint32_t v[32];
-                tc_ld32(tD2 + lane_addr + j * 32, v);
+                tc_ld32(tD2 + lane_addr + half * 64 + j * 32, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
@@ -291,27 +293,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
             }
             g_first = false;
-            ++n_drained;
             tc_fence_before();
             tc_mbar_arrive(g_empty);
         };
         for (long long s = 0; s < my_slabs; ++s) {
             const int b = (int)(s & 1);
-            const long long row0 = (blockIdx.x + s * gridDim.x) * kTcRows;
-            if (s > 0 && (s % kTcDrain) == 0) drain();
+            const long long row0 = (blockIdx.x + s * gridDim.x) * kTcRows + half * 64;
             tc_mbar_wait(&eta_full[b], (uint32_t)((s >> 1) & 1));
             tc_fence_after();
             float lp_s = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {  // 32 rows of the slab at a time
+            uint32_t rh[2][16], rl[2][16];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {  // 32 rows of the slab at a time
                 uint32_t v[32];
-                tc_ld32(tD1[b] + lane_addr + j * 32, v);
+                tc_ld32(tD1[b] + lane_addr + half * 64 + j * 32, v);
                 tc_wait_ld();
-                if (j == 3) {  // D1[b] has been read completely: GEMM 1 of slab s + 2 may overwrite it
+                if (j == 1) {  // this thread's share of D1[b] has been read: GEMM 1 of slab s + 2 may overwrite it
                     tc_fence_before();
                     tc_mbar_arrive(&eta_empty[b]);
                 }
-                uint32_t rh[16], rl[16];
                 const long long r_base = row0 + j * 32;
                 // y of these 32 rows: one 32-byte global read, the same address for every thread (L1 broadcast)
                 uint32_t yw[8];
@@ -337,39 +337,41 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const float x = __uint_as_float(v[i + u]);
                         const float yi = (float)((yw[(i + u) >> 2] >> (8 * ((i + u) & 3))) & 0xff);
                         const bool live = r_base + i + u < A.N;
-                        // accurate (not fast-math) expf / log1pf: the fast intrinsics carry a BIAS of ~3e-7 per row that
-                        // adds up linearly in the log-likelihood (measured: 6e-7 relative at 8192 rows); ~1 ulp errors do not
-                        const float e = expf(-fabsf(x));
-                        const float inv = 1.f / (1.f + e);
+                        const float e = __expf(-fabsf(x));                     // 2 ulp: unbiased, enters sigmoid and log1p only
+                        const float inv = __fdividef(1.f, 1.f + e);
                         const float sg = x >= 0.f ? inv : e * inv;            // sigmoid(x)
-                        const float sp = fmaxf(x, 0.f) + log1pf(e);           // softplus(x)
+                        const float sp = fmaxf(x, 0.f) + log1pf(e);           // softplus(x): the accurate log1p (summed over N rows)
                         lp_s += live ? fmaf(yi, x, -sp) : 0.f;
                         rr[u] = live ? yi - sg : 0.f;
                     }
                     const __half2 h = __floats2half2_rn(rr[0], rr[1]);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(rr[0] - hf.x, rr[1] - hf.y);
-                    rh[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                    rl[i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+                    rh[j][i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    rl[j][i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
                 }
-                if (j == 0 && s > 0) {  // GEMM 2 of slab s - 1 must have consumed the previous r before it is overwritten
-                    tc_mbar_wait(r_empty, (uint32_t)((s - 1) & 1));
-                    tc_fence_after();
-                }
-                tc_st16(tRh + lane_addr + j * 16, rh);
-                tc_st16(tRl + lane_addr + j * 16, rl);
+            }
+            // GEMM 2 of the previous slab has finished by now (it ran under the arithmetic above): its gradient goes to fp64,
+            // which also frees r for this slab
+            if (s > 0) drain(s - 1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                tc_st16(tRh + lane_addr + half * 32 + j * 16, rh[j]);
+                tc_st16(tRl + lane_addr + half * 32 + j * 16, rl[j]);
             }
             tc_wait_st();
             tc_fence_before();
             tc_mbar_arrive(r_full);
             lp += (double)lp_s;
         }
-        if (my_slabs > 0) drain();
+        if (my_slabs > 0) drain(my_slabs - 1);
         else {
-            double* gp = A.Gpart + gp_off;
-            for (int k = 0; k < kTcK; ++k) gp[k] = 0.0;
+            for (int k = 0; k < 64; ++k) gp[k] = 0.0;
         }
-        A.lpart[(long long)blockIdx.x * A.Cpad + c_base + c] = lp;
+        if (half == 1) lp_half_s[c] = lp;
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"r"(kTcEpiThreads) : "memory");  // the 8 epilogue warps only
+        if (half == 0) A.lpart[(long long)blockIdx.x * A.Cpad + c_base + c] = lp + lp_half_s[c];
     }
     tc_fence_before();
     __syncthreads();

@@ -97,9 +97,9 @@ class CompiledModel:
             import scipy.linalg as sl
 
             L = np.ascontiguousarray(data["L"], dtype=np.float64)
-            Linv = sl.solve_triangular(L, np.eye(L.shape[0]), lower=True)
+            LinvT = data["LinvT"] if "LinvT" in data else sl.solve_triangular(L, np.eye(L.shape[0]), lower=True).T
             d.x, d.aux = hold(data["prec"], np.float64), hold(data["cov"], np.float64)
-            d.m1, d.m2 = hold(Linv.T, np.float64), hold(L, np.float64)
+            d.m1, d.m2 = hold(LinvT, np.float64), hold(L, np.float64)
             d.scalar0 = spec.meta["logdet_L"]
         elif spec.name == "ir":
             c_ir, keep_ir = _lib.build_ir(_ir.lower(self.ir))
@@ -119,6 +119,19 @@ class CompiledModel:
         self.supports_constrain = hasattr(self._lib, "b200_model_set_transforms")
         if self.supports_constrain:
             _lib.check(self._lib.b200_model_set_transforms(self._h, kind.ctypes.data, lo.ctypes.data, hi.ctypes.data))
+
+    def pointwise_loglik(self, draws, lik: int = 0):
+        """log p(y_i | draw) for every draw: ``draws[..., n]`` (unconstrained) -> ``[..., N]`` (IR models on the generic
+        device function).  The `log_likelihood` group pm.compute_log_likelihood builds (pymc/stats/log_density.py:31-77)."""
+        if self.spec.name != "ir":
+            raise NotImplementedError("pointwise_loglik needs a model compiled from ModelIR with specialise=False")
+        q = _f64(draws)
+        lead = q.shape[:-1]
+        q2 = q.reshape(-1, self.n)
+        N = len(self.ir.likelihoods[lik].y)
+        out = np.empty((q2.shape[0], N))
+        _lib.check(self._lib.b200_pointwise_loglik(self._h, int(lik), q2.ctypes.data, q2.shape[0], out.ctypes.data, _lib.MEM_HOST, None))
+        return out.reshape(lead + (N,))
 
     def set_dense_mass(self, cov=None, *, inverse=None) -> None:
         """Fixed dense mass matrix for ``nuts_run(mass="dense")``: ``cov`` -> QuadPotentialFull(cov) (quadpotential.py:680-725),

@@ -230,26 +230,45 @@ def stochvol(T: int = 3000, seed: int = 4) -> ModelSpec:
 # ------------------------------------------------------------------------------------------------
 # config 5: correlated Gaussian, dense covariance
 # ------------------------------------------------------------------------------------------------
-def mvgauss(n: int = 10_000, seed: int = 5) -> ModelSpec:
-    """x~MvNormal(0, chol=L).  Stores L, Sigma=L L^T and the precision P=Sigma^-1 (the gradient is -P x)."""
+def mvgauss(n: int = 10_000, seed: int = 5, cache_dir: str | None = None) -> ModelSpec:
+    """x~MvNormal(0, chol=L).  Stores L, Sigma=L L^T, the precision P=Sigma^-1 (the gradient is -P x) and L^-T (momentum
+    draws of the dense mass matrix).  ``cache_dir``: keep the four n x n matrices on disk (e.g. /dev/shm) -- building them
+    for n = 10^4 costs about a minute of BLAS time, and every rank of a multi-GPU run needs them."""
+    import os
+
     import scipy.linalg as sl
 
-    rng = np.random.default_rng(seed)
-    d = np.exp(rng.normal(0.0, 0.5, n))
-    L = np.tril(rng.standard_normal((n, n)), -1) * (0.05 / np.sqrt(n))
-    L[np.diag_indices(n)] = d
-    Linv = sl.solve_triangular(L, np.eye(n), lower=True)
-    P = Linv.T @ Linv
-    P = 0.5 * (P + P.T)
-    cov = L @ L.T
-    cov = 0.5 * (cov + cov.T)
+    path = os.path.join(cache_dir, f"b200_mvgauss_n{n}_s{seed}.npz") if cache_dir else None
+    if path and os.path.isfile(path):
+        z = np.load(path)
+        L, cov, P, LinvT, logdet = z["L"], z["cov"], z["prec"], z["LinvT"], float(z["logdet_L"])
+    else:
+        rng = np.random.default_rng(seed)
+        d = np.exp(rng.normal(0.0, 0.5, n))
+        L = np.tril(rng.standard_normal((n, n)), -1) * (0.05 / np.sqrt(n))
+        L[np.diag_indices(n)] = d
+        Linv = sl.solve_triangular(L, np.eye(n), lower=True)
+        P = Linv.T @ Linv
+        P = 0.5 * (P + P.T)
+        cov = L @ L.T
+        cov = 0.5 * (cov + cov.T)
+        LinvT = np.ascontiguousarray(Linv.T)
+        logdet = float(np.sum(np.log(d)))
+        if path:
+            try:
+                os.makedirs(cache_dir, exist_ok=True)
+                tmp = f"{path}.{os.getpid()}.tmp.npz"
+                np.savez(tmp, L=L, cov=cov, prec=P, LinvT=LinvT, logdet_L=logdet)
+                os.replace(tmp, path)
+            except OSError:
+                pass
     vars_, n_ = _layout([("x", "x", n, None, None)])
     return ModelSpec(
         KIND_MVGAUSS,
         n_,
         vars_,
-        data={"L": L, "cov": cov, "prec": P},
-        meta={"logdet_L": float(np.sum(np.log(d)))},
+        data={"L": L, "cov": cov, "prec": P, "LinvT": LinvT},
+        meta={"logdet_L": logdet},
     )
 
 

@@ -1,5 +1,5 @@
 """ncu targets for the lock-step (GEMM-shaped) engine: a few batched leapfrogs at full size.
-usage: ncu_target3.py logistic|logistic_tc|mvgauss [tune draws]"""
+usage: ncu_target3.py logistic|logistic_tc|mvgauss|mvgauss_tc [tune draws]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,9 +10,9 @@ r = np.random.default_rng(1)
 if which in ("logistic", "logistic_tc"):
     spec = models.logistic(); C, kw = 512, {}
 else:
-    spec = models.mvgauss(); C, kw = 256, dict(mass="dense")
+    spec = models.mvgauss(cache_dir="/dev/shm/b200_cache"); C, kw = 256, dict(mass="dense")
 cm = engine.CompiledModel(spec)
-if which == "logistic_tc":
+if which in ("logistic_tc", "mvgauss_tc"):
     cm.set_precision("tc_fp16x2")
 q0 = spec.initial_point() + r.uniform(-1, 1, (C, spec.n))
 sr, pr, _ = brng.chain_generators(5, C)

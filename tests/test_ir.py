@@ -247,3 +247,34 @@ def test_new_model_runs_with_no_new_cuda_and_matches_the_oracle_sampler():
     assert np.max(np.abs(xo.mean(0) - xg.mean(0)) / se) < 5.0
     assert np.all(np.abs(np.log(xo.std(0) / xg.std(0))) < 0.25)
     assert run.stats["diverging"].mean() < 0.02
+
+
+@pytest.mark.gpu
+def test_pointwise_log_likelihood_matches_oracle_and_sums_to_the_likelihood_term():
+    """pm.compute_log_likelihood's group (pymc/stats/log_density.py:31-77) from the device: log p(y_i | draw) per draw."""
+    from scipy import stats as st
+
+    from pymc_b200 import engine
+
+    m = ir.radon_ir(60, 5, 3)
+    cm = engine.CompiledModel(m, specialise=False)
+    rng = np.random.default_rng(4)
+    q = m.initial_point() + rng.uniform(-0.5, 0.5, (3, 7, m.n))
+    ll = cm.pointwise_loglik(q)
+    assert ll.shape == (3, 7, 60)
+    c = m.constrain(q)
+    L = m.likelihoods[0]
+    county, floor = L.terms[1].factors[1][1], L.terms[2].coef
+    mu = (c["mu_a"][..., None] + c["sigma_a"][..., None] * c["a"][..., county]
+          + (c["mu_b"][..., None] + c["sigma_b"][..., None] * c["b"][..., county]) * floor)
+    want = st.norm(mu, c["eps"][..., None]).logpdf(L.y)
+    np.testing.assert_allclose(ll, want, rtol=1e-12, atol=1e-12)
+    m2 = ir.varying_intercept_logistic_ir()
+    cm2 = engine.CompiledModel(m2)
+    q2 = rng.uniform(-1, 1, (5, m2.n))
+    ll2 = cm2.pointwise_loglik(q2)
+    c2 = m2.constrain(q2)
+    L2 = m2.likelihoods[0]
+    eta = c2["alpha"][:, L2.terms[0].factors[0][1]] + sum(c2["beta"][:, [k]] * L2.terms[1 + k].coef for k in range(3))
+    want2 = L2.y * eta - np.logaddexp(0.0, eta)
+    np.testing.assert_allclose(ll2, want2, rtol=1e-12, atol=1e-13)

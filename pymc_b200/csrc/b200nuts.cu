@@ -109,6 +109,17 @@ struct b200_model {
     // tens of milliseconds of host time on the end-to-end path)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* ls_arena = nullptr;  // lock-step engine: per-chain state machines, vectors, request matrices (kept between runs)
+    size_t ls_arena_bytes = 0;
+    cudaError_t ensure_ls_arena(size_t bytes) {
+        if (bytes <= ls_arena_bytes) return cudaSuccess;
+        if (ls_arena) cudaFree(ls_arena);
+        ls_arena = nullptr;
+        ls_arena_bytes = 0;
+        cudaError_t e = cudaMalloc(&ls_arena, bytes);
+        if (e == cudaSuccess) ls_arena_bytes = bytes;
+        return e;
+    }
     cudaError_t ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return cudaSuccess;
         if (scratch) cudaFree(scratch);
@@ -119,6 +130,7 @@ struct b200_model {
         return e;
     }
     ~b200_model() {
+        if (ls_arena) cudaFree(ls_arena);
         if (tc_a_hi) cudaFree(tc_a_hi);
         if (tc_a_lo) cudaFree(tc_a_lo);
         if (ir_scratch) cudaFree(ir_scratch);
@@ -989,7 +1001,8 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
     }
     if (rc) return rc;
     logistic_finish_kernel<<<(C + 3) / 4, 128, 0, st>>>(Q, ld, G, ld, n, m->KP, C, bs.cpad, bs.gpart.as<double>(),
-                                                        bs.lpart.as<double>(), gx, logp);
+                                                        bs.lpart.as<double>(), gx, logp,
+                                                        m->precision == B200_PRECISION_TC_FP16X2 ? 1 : 0);
     CU(cudaGetLastError());
     if (launches) *launches += 2;
     return 0;
@@ -1021,23 +1034,37 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     const bool dense = P.dense != 0;
     const long long ld = m->ld;
     const size_t mat = (size_t)C * ld * sizeof(double);
-    DevBuf state, vecs, Qreq, Greq, Wreq, lreq, P0n, V0n, counters, mom_list, Zb, P0b, V0b;
+    // One arena in the model handle, kept between runs (eleven cudaMalloc per run; the chain vectors alone
+    // are 2.6 GB for config 5, and allocating / freeing them cost ~1 s of host time per run): state | vecs | 3-8 request
+    // matrices | logp | counters | momentum list.
     P.ld = ld;
     P.vec_stride = ls_vec_count(P.max_td) * n;
-    CU(state.alloc((size_t)C * sizeof(LsState)));
-    CU(vecs.alloc((size_t)C * P.vec_stride * sizeof(double)));
-    CU(Qreq.alloc(mat)); CU(Greq.alloc(mat)); CU(lreq.alloc((size_t)C * sizeof(double)));
-    CU(counters.alloc(2 * sizeof(int))); CU(mom_list.alloc((size_t)C * sizeof(int)));
-    CU(cudaMemsetAsync(Qreq.p, 0, mat, st)); CU(cudaMemsetAsync(Greq.p, 0, mat, st));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_state = up((size_t)C * sizeof(LsState)), b_vecs = up((size_t)C * P.vec_stride * sizeof(double)), b_mat = up(mat);
+    const size_t b_l = up((size_t)C * sizeof(double)), b_cnt = up(2 * sizeof(int)), b_mom = up((size_t)C * sizeof(int));
+    const int n_mats = dense ? 8 : 2;
+    CU(m->ensure_ls_arena(b_state + b_vecs + n_mats * b_mat + b_l + b_cnt + b_mom));
+    char* a = static_cast<char*>(m->ls_arena);
+    auto take = [&](size_t b) { char* p = a; a += b; return p; };
+    P.state = reinterpret_cast<LsState*>(take(b_state));
+    P.vecs = reinterpret_cast<double*>(take(b_vecs));
+    P.Qreq = reinterpret_cast<double*>(take(b_mat));
+    P.Greq = reinterpret_cast<double*>(take(b_mat));
+    double *Zb = nullptr, *P0b = nullptr, *V0b = nullptr;
     if (dense) {
-        CU(Wreq.alloc(mat)); CU(P0n.alloc(mat)); CU(V0n.alloc(mat)); CU(Zb.alloc(mat)); CU(P0b.alloc(mat)); CU(V0b.alloc(mat));
-        CU(cudaMemsetAsync(Wreq.p, 0, mat, st)); CU(cudaMemsetAsync(Zb.p, 0, mat, st));
+        P.Wreq = reinterpret_cast<double*>(take(b_mat));
+        P.P0n = reinterpret_cast<double*>(take(b_mat));
+        P.V0n = reinterpret_cast<double*>(take(b_mat));
+        Zb = reinterpret_cast<double*>(take(b_mat));
+        P0b = reinterpret_cast<double*>(take(b_mat));
+        V0b = reinterpret_cast<double*>(take(b_mat));
     }
-    CU(cudaMemsetAsync(vecs.p, 0, (size_t)C * P.vec_stride * sizeof(double), st));
-    P.state = state.as<LsState>(); P.vecs = vecs.as<double>();
-    P.Qreq = Qreq.as<double>(); P.Greq = Greq.as<double>(); P.Wreq = Wreq.as<double>(); P.logp_req = lreq.as<double>();
-    P.P0n = P0n.as<double>(); P.V0n = V0n.as<double>();
-    P.counters = counters.as<int>(); P.mom_list = mom_list.as<int>();
+    P.logp_req = reinterpret_cast<double*>(take(b_l));
+    P.counters = reinterpret_cast<int*>(take(b_cnt));
+    P.mom_list = reinterpret_cast<int*>(take(b_mom));
+    // the padding columns of the request / result matrices must be zero (they are inside the GEMMs' k range) and the chain
+    // vectors start from zero: clearing is bandwidth-trivial (2.6 GB at HBM speed = 0.4 ms), unlike allocating
+    CU(cudaMemsetAsync(P.vecs, 0, b_vecs + n_mats * b_mat, st));
     P.logp_from_dot = (m->kind == B200_MODEL_MVGAUSS) ? 1 : 0;
     P.logp_const = m->logp_const;
     BatchScratch bs;
@@ -1055,11 +1082,11 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
             if (gemm_nt(m, st, P.Greq, ld, C, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
             ++launches;
             if (n_mom > 0) {
-                ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb.as<double>());
+                ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb);
                 // p0 = L^-T z (solve_triangular(chol.T, z), quadpotential.py:710-713);  v0 = Sigma p0 = L z
-                if (gemm_nt(m, st, Zb.as<double>(), ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b.as<double>(), ld)) return -1;
-                if (gemm_nt(m, st, Zb.as<double>(), ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b.as<double>(), ld)) return -1;
-                ls_scatter_mom_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, P0b.as<double>(), V0b.as<double>());
+                if (gemm_nt(m, st, Zb, ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b, ld)) return -1;
+                if (gemm_nt(m, st, Zb, ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b, ld)) return -1;
+                ls_scatter_mom_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, P0b, V0b);
                 CU(cudaGetLastError());
                 launches += 4;
             }

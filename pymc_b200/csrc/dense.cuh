@@ -288,14 +288,15 @@ __global__ void __launch_bounds__(32 * (kLogiChains / (8 * MB)), 1)
 __global__ void __launch_bounds__(128) logistic_finish_kernel(const double* __restrict__ Q, long long ldq, double* __restrict__ G,
                                                               long long ldg, int K, int KP, int C, int Cpad,
                                                               const double* __restrict__ Gpart, const double* __restrict__ lpart,
-                                                              int nparts, double* __restrict__ logp) {
+                                                              int nparts, double* __restrict__ logp, int feature_major = 0) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     double s = 0.0;
     for (int k = lane; k < K; k += 32) {
         double a = 0.0;
-        for (int p = 0; p < nparts; ++p) a += Gpart[((long long)p * Cpad + c) * KP + k];
+        for (int p = 0; p < nparts; ++p)
+            a += feature_major ? Gpart[((long long)p * KP + k) * Cpad + c] : Gpart[((long long)p * Cpad + c) * KP + k];
         const double b = Q[(long long)c * ldq + k];
         G[(long long)c * ldg + k] = a - b;
         s = fma(b, b, s);

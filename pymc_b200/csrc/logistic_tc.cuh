@@ -34,6 +34,7 @@ constexpr int kTcK = 128;         // features (padded)
 constexpr int kTcStages = 2;      // X slab stages in shared memory
 constexpr int kTcThreads = 320;   // 10 warps: TMA producer, MMA issuer, 8 epilogue
 constexpr int kTcEpiThreads = 256;
+constexpr int kTcDrain = 2;       // slabs per fp32 gradient accumulation chunk (16 full-magnitude accumulate steps)
 constexpr uint32_t kTcBlockBytes = kTcRows * 64 * 2;          // one [128 rows][64 cols] fp16 box = 16 KB
 constexpr uint32_t kTcPieceBytes = 2 * kTcBlockBytes;         // one piece of a [128][128] tile = 32 KB
 constexpr uint32_t kTcStageBytes = 2 * kTcPieceBytes;         // X_hi + X_lo = 64 KB
@@ -140,7 +141,7 @@ struct LogisticTcArgs {
     const double* Q;         // [C][ldq] beta per chain
     long long ldq;
     int C, K;
-    double* Gpart;           // [gridDim.x][Cpad][128]
+    double* Gpart;           // [gridDim.x][128 features][Cpad]  (feature-major, see the drain)
     double* lpart;           // [gridDim.x][Cpad]
     int Cpad;
 };
@@ -149,7 +150,7 @@ struct LogisticTcArgs {
 // tcgen05.mma into an accumulator of magnitude |D| loses ~2^-25 |D| one-sidedly (measured, round 2 call 3: 24 accumulate
 // steps per slab -> 8e-7, 384 steps -> 7.9e-6 relative).  So (i) the small correction products hi*lo and lo*hi are issued
 // FIRST, while the accumulator is still tiny, and hi*hi last: 8 full-magnitude steps per GEMM instead of 24; (ii) the
-// gradient accumulator is drained into fp64 after EVERY slab.
+// gradient accumulator is drained into fp64 every kTcDrain = 2 slabs.
 __global__ void __launch_bounds__(kTcThreads, 1)
     logistic_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const LogisticTcArgs A) {
     extern __shared__ char tc_smem_raw[];
@@ -162,8 +163,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint64_t* eta_full = bars + 4;    // [2] MMA (GEMM 1 done) -> epilogue
     uint64_t* eta_empty = bars + 6;   // [2] epilogue (D1 read) -> MMA
     uint64_t* r_full = bars + 8;      // epilogue (r written) -> MMA
-    uint64_t* g_full = bars + 9;      // MMA (GEMM 2 of a slab done: D2 complete, r and the X stage free) -> epilogue
-    uint64_t* g_empty = bars + 10;    // epilogue (D2 drained) -> MMA
+    uint64_t* r_empty = bars + 9;     // MMA (GEMM 2 done: r and the X stage are free) -> epilogue
+    uint64_t* g_full = bars + 10;     // MMA (drain point reached: D2 holds kTcDrain slabs) -> epilogue
+    uint64_t* g_empty = bars + 11;    // epilogue (D2 drained) -> MMA
     __shared__ uint32_t tmem_base_s;
     __shared__ double lp_half_s[kTcChains];
 
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(&eta_empty[i], kTcEpiThreads);
         }
         mbar_init(r_full, kTcEpiThreads);
+        mbar_init(r_empty, 1);
         mbar_init(g_full, 1);
         mbar_init(g_empty, kTcEpiThreads);
     }
@@ -250,11 +253,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (s + 1 < my_slabs) gemm1(s + 1);
                 // GEMM 2 of slab s: D2 = r . X   (A = r pieces in TMEM, B = X pieces read MN-major); D2 was drained
                 tc_mbar_wait(r_full, (uint32_t)(s & 1));
-                if (s > 0) tc_mbar_wait(g_empty, (uint32_t)((s - 1) & 1));
+                const bool first = (s % kTcDrain) == 0;   // D2 was drained before this slab
+                if (first && s > 0) tc_mbar_wait(g_empty, (uint32_t)(((s / kTcDrain) - 1) & 1));
                 tc_fence_after();
                 const int st = (int)(s % kTcStages);
                 const uint32_t xa = smem_u32(x_s + st * kTcStageBytes);
-                uint32_t acc = 0;
+                uint32_t acc = first ? 0u : 1u;
 #pragma unroll
                 for (int prod = 0; prod < 3; ++prod) {  // r_hi X_lo, r_lo X_hi, r_hi X_hi
                     const uint32_t ta = (prod == 1) ? tRl : tRh;
@@ -266,7 +270,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                 }
                 tc_commit(&x_empty[st]);
-                tc_commit(g_full);
+                tc_commit(r_empty);
+                if ((s + 1) % kTcDrain == 0 || s + 1 == my_slabs) tc_commit(g_full);
             }
         }
     } else {
@@ -276,10 +281,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int c = sub * 32 + lane;                       // chain inside the CTA = TMEM lane
         const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
         double lp = 0.0;
-        double* gp = A.Gpart + ((long long)blockIdx.x * A.Cpad + c_base + c) * kTcK + half * 64;
+        // this CTA's fp64 partial gradient, FEATURE-major [128 k][Cpad chains]: for a fixed k the 32 lanes of a warp touch 32
+        // consecutive chains (coalesced read-modify-write in L2; the chain-major layout cost 5 ms per batch, measured)
+        double* gp = A.Gpart + ((long long)blockIdx.x * kTcK + half * 64) * A.Cpad + c_base + c;
         bool g_first = true;
-        auto drain = [&](long long s_done) {  // fp32 gradient of slab s_done -> this CTA's fp64 partial (global, L2 resident)
-            tc_mbar_wait(g_full, (uint32_t)(s_done & 1));
+        long long n_drains = 0;
+        auto drain = [&]() {  // fp32 gradient accumulator -> fp64 partial
+            tc_mbar_wait(g_full, (uint32_t)(n_drains & 1));
             tc_fence_after();
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
@@ -289,10 +297,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const double add = (double)__uint_as_float(v[k]);
-                    gp[j * 32 + k] = g_first ? add : gp[j * 32 + k] + add;
+                    double* e = gp + (long long)(j * 32 + k) * A.Cpad;
+                    *e = g_first ? add : *e + add;
                 }
             }
             g_first = false;
+            ++n_drains;
             tc_fence_before();
             tc_mbar_arrive(g_empty);
         };
@@ -351,9 +361,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     rl[j][i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
                 }
             }
-            // GEMM 2 of the previous slab has finished by now (it ran under the arithmetic above): its gradient goes to fp64,
-            // which also frees r for this slab
-            if (s > 0) drain(s - 1);
+            // GEMM 2 of the previous slab has finished by now (it ran under the arithmetic above), which frees r for this slab;
+            // every kTcDrain slabs its accumulator goes to fp64
+            if (s > 0) {
+                if (s % kTcDrain == 0) drain();
+                else {
+                    tc_mbar_wait(r_empty, (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 tc_st16(tRh + lane_addr + half * 32 + j * 16, rh[j]);
@@ -364,9 +380,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tc_mbar_arrive(r_full);
             lp += (double)lp_s;
         }
-        if (my_slabs > 0) drain(my_slabs - 1);
+        if (my_slabs > 0) drain();
         else {
-            for (int k = 0; k < 64; ++k) gp[k] = 0.0;
+            for (int k = 0; k < 64; ++k) gp[(long long)k * A.Cpad] = 0.0;
         }
         if (half == 1) lp_half_s[c] = lp;
         __syncwarp();

@@ -28,6 +28,14 @@ namespace b200 {
 
 constexpr int kLsLevels = 12;
 
+// the O(n) vector passes of the advance kernel are latency-bound strided loops: unrolling keeps several loads in flight
+#ifndef B200_LS_UNROLL_N
+#define B200_LS_UNROLL_N 4
+#endif
+#define B200_LS_PRAGMA(x) _Pragma(#x)
+#define B200_LS_UNROLL_(n) B200_LS_PRAGMA(unroll n)
+#define B200_LS_UNROLL B200_LS_UNROLL_(B200_LS_UNROLL_N)
+
 struct LsState {  // per-chain scalars, resident in HBM between calls
     int phase;    // 0 = INIT (waiting for the evaluation at q0), 1 = LEAF (waiting for a leapfrog's evaluation), 2 = DONE
     int it, d_iter, maxd, depth, leaf, n_leaf, dir, w_idx, L_idx, R_idx, n_prop, m_pidx, c_pidx;
@@ -103,6 +111,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     auto req_logp = [&]() -> double {
         if (P.logp_from_dot) {
             double s = 0.0;
+            B200_LS_UNROLL
             for (int i = lane; i < n; i += TS) s = fma(qreq[i], greq[i], s);
             return P.logp_const + 0.5 * team_sum<W>(s, lane, red);
         }
@@ -114,6 +123,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     if (S.phase == 0) {
         // ---- evaluation at q0 has arrived: the start state of the first draw --------------------------------
         S.cur_logp = req_logp();
+        B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) {
             V(LV_Q)[i] = qreq[i];
             V(LV_G)[i] = greq[i];
@@ -129,6 +139,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         {
             double* p = V(LV_P); double* v = V(LV_V); double* q = V(LV_Q); double* g = V(LV_G); double* w = V(LV_W);
             const double* var = V(LV_VAR);
+            B200_LS_UNROLL
             for (int i = lane; i < n; i += TS) {
                 const double gi = greq[i];
                 const double pi = fma(dt, gi, p[i]);
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             sub_div = true;
         } else {
             // the leaf as a height-0 subtree
+            B200_LS_UNROLL
             for (int i = lane; i < n; i += TS) {
                 const double pi = V(LV_P)[i];
                 V(LV_CLP)[i] = pi; V(LV_CPS)[i] = pi; V(LV_CLV)[i] = V(LV_V)[i];
@@ -169,6 +181,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 double* c_lp = V(LV_CLP); double* c_lv = V(LV_CLV); double* c_ps = V(LV_CPS);
                 const double* wp = V(LV_P); const double* wv = V(LV_V);
                 double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) {
                     const double tl = t_lp[i], tlv = t_lv[i], tr = t_rp[i], trv = t_rv[i], tp = t_ps[i];
                     const double cl = c_lp[i], clv = c_lv[i], cp = c_ps[i];
@@ -195,6 +208,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 const double u = rng.next_double();
                 if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                     const double* t_pq = LVL(h, 5); const double* t_pqg = LVL(h, 6); const double* t_pqw = LVL(h, 7);
+                    B200_LS_UNROLL
                     for (int i = lane; i < n; i += TS) {
                         V(LV_CPQ)[i] = t_pq[i]; V(LV_CPQG)[i] = t_pqg[i];
                         if (dense) V(LV_CPQW)[i] = t_pqw[i];
@@ -206,6 +220,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             }
             if (!sub_turn && S.leaf + 1 < S.n_leaf) {
                 // park the finished subtree (height h) until its right sibling is built
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) {
                     LVL(h, 0)[i] = V(LV_CLP)[i]; LVL(h, 1)[i] = V(LV_CLV)[i];
                     LVL(h, 2)[i] = V(LV_P)[i];   LVL(h, 3)[i] = V(LV_V)[i];
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 // new outer edge = integrator state
                 {
                     const int b = dir > 0 ? LV_RQ : LV_LQ;
+                    B200_LS_UNROLL
                     for (int i = lane; i < n; i += TS) {
                         V(b + 0)[i] = V(LV_Q)[i]; V(b + 1)[i] = V(LV_P)[i]; V(b + 2)[i] = V(LV_G)[i];
                         V(b + 3)[i] = V(LV_V)[i];
@@ -242,6 +258,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                     const double dlw = S.c_logw - S.m_logw;
                     const double e_w = exp(-fabs(dlw));
                     if (dlw >= 0.0 || u < e_w) {
+                        B200_LS_UNROLL
                         for (int i = lane; i < n; i += TS) {
                             V(LV_PQ)[i] = V(LV_CPQ)[i]; V(LV_PQG)[i] = V(LV_CPQG)[i];
                             if (dense) V(LV_PQW)[i] = V(LV_CPQW)[i];
@@ -259,6 +276,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                     const double* cps = V(LV_CPS); const double* clp = V(LV_CLP); const double* clv = V(LV_CLV);
                     const double* wv = V(LV_V);
                     double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    B200_LS_UNROLL
                     for (int i = lane; i < n; i += TS) {
                         const double so = PS[i], cp = cps[i];
                         const double s = so + cp;
@@ -294,6 +312,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         const bool rec = P.store_warmup || !tuning;
         const int t_out = P.store_warmup ? S.it : S.it - P.tune;
         // accepted position (+ its gradient, Sigma.gradient and logp) becomes the chain state
+        B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) {
             const double qi = V(LV_PQ)[i];
             V(LV_Q)[i] = qi; V(LV_G)[i] = V(LV_PQG)[i];
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             if (S.k_samples > P.discard) {
                 S.fg_n += 1.0; S.bg_n += 1.0;
                 double* fm = V(S.fg_m); double* fv = V(S.fg_v); double* bm = V(S.bg_m); double* bv = V(S.bg_v);
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) {
                     const double x = V(LV_Q)[i];
                     double mean = fm[i], d0 = x - mean;
@@ -325,12 +345,14 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             }
             if (S.k_samples > S.window) {
                 const double* fv = V(S.fg_v);
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) V(LV_VAR)[i] = fmin(fmax(fv[i] / S.fg_n, 1e-12), 1e12);
             }
             if (S.k_samples > 0 && S.k_samples % S.window == 0) {
                 const int tm = S.fg_m, tv = S.fg_v;
                 S.fg_m = S.bg_m; S.fg_v = S.bg_v; S.fg_n = S.bg_n;
                 S.bg_m = tm; S.bg_v = tv; S.bg_n = 0.0;
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) { V(S.bg_m)[i] = 0.0; V(S.bg_v)[i] = 0.0; }
             }
             ++S.k_samples;
@@ -365,9 +387,11 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             double* p = V(LV_P); double* v = V(LV_V);
             if (dense) {
                 const double* p0 = P.P0n + (long long)chain * P.ld; const double* v0 = P.V0n + (long long)chain * P.ld;
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) { const double pi = p0[i], vi = v0[i]; p[i] = pi; v[i] = vi; kin = fma(pi, vi, kin); }
             } else {
                 const double* var = V(LV_VAR);
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) {
                     const double zz = (P.momentum_source == B200_MOMENTUM_HOST_BUFFER)
                                           ? P.z[((long long)chain * Ttot + S.it) * n + i]
@@ -384,12 +408,14 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             for (int t = S.it; t < Ttot; ++t) {
                 if (!(P.store_warmup || t >= P.tune)) continue;
                 const int t_o = P.store_warmup ? t : t - P.tune;
+                B200_LS_UNROLL
                 for (int i = lane; i < n; i += TS) P.draws_out[((long long)chain * T_out + t_o) * n + i] = nan("");
                 if (lane == 0) stats_sentinel(P.st, (long long)chain * T_out + t_o);
             }
         } else {
             S.eps = exp(adapting ? S.log_step : S.log_bar);
             S.maxd = (tuning && S.it < 200) ? P.early_td : P.max_td;
+            B200_LS_UNROLL
             for (int i = lane; i < n; i += TS) {
                 const double qi = V(LV_Q)[i], pi = V(LV_P)[i], gi = V(LV_G)[i], vi = V(LV_V)[i];
                 V(LV_LQ)[i] = qi; V(LV_RQ)[i] = qi; V(LV_PQ)[i] = qi;
@@ -410,6 +436,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         team_sync<W>();
         S.dir = (rng.next_double() < 0.5) ? 1 : -1;  // nuts.py:215
         const int b = S.dir > 0 ? LV_RQ : LV_LQ;
+        B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) {
             V(LV_Q)[i] = V(b + 0)[i];
             const double pi = V(b + 1)[i], vi = V(b + 3)[i];
@@ -429,6 +456,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         const double es = S.dir * S.eps, dt = 0.5 * es;
         double* p = V(LV_P); double* v = V(LV_V);
         const double* q = V(LV_Q); const double* g = V(LV_G); const double* w = V(LV_W); const double* var = V(LV_VAR);
+        B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) {
             const double pi = fma(dt, g[i], p[i]);
             const double vi = dense ? fma(dt, w[i], v[i]) : var[i] * pi;
@@ -455,6 +483,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         *SP = S;
     }
     if (S.phase == 2 && P.sm.final_var)
+        B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) P.sm.final_var[(long long)chain * n + i] = V(LV_VAR)[i];
 }
 

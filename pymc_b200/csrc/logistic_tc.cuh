@@ -350,7 +350,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const float e = __expf(-fabsf(x));                     // 2 ulp: unbiased, enters sigmoid and log1p only
                         const float inv = __fdividef(1.f, 1.f + e);
                         const float sg = x >= 0.f ? inv : e * inv;            // sigmoid(x)
-                        const float sp = fmaxf(x, 0.f) + log1pf(e);           // softplus(x): the accurate log1p (summed over N rows)
+                        // softplus(x) = max(x, 0) + log(1 + e), 1 + e in (1, 2]: lg2.approx there is good to 2^-22 absolute, four
+                        // times coarser than log1pf but 25 instructions cheaper per element (the epilogue bounds this kernel);
+                        // summed over 1e6 rows that is ~3e-10 of logp, far below the tensor cores' accumulate rounding (1.5e-7)
+                        const float sp = fmaxf(x, 0.f) + __logf(1.f + e);
                         lp_s += live ? fmaf(yi, x, -sp) : 0.f;
                         rr[u] = live ? yi - sg : 0.f;
                     }

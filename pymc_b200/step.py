@@ -83,6 +83,7 @@ class B200NUTS:
         self._tune_n = self._draws_n = None
         self._res = None
         self._base, self._served, self._bad_at, self._resume_eps, self._pot_rng = 0, None, -1, None, None
+        self._state = None
 
     # ---- BlockedStep protocol (step_methods/compound.py:132-250) -------------------------------------------------
     @staticmethod
@@ -134,8 +135,13 @@ class B200NUTS:
         eps0 = None
         if self._resume_eps is not None:  # re-launch mid-chain: continue from the step size adapted so far
             eps0 = np.array([self._resume_eps])
+        from .engine import ChainState
+
+        self._state = ChainState(1, self.spec.n) if hasattr(self._cm, "_h") else None  # engines that export chain state
+        extra = {"save": self._state} if self._state is not None else {}
         self._res = self._cm.nuts_run(q0[None, :], states, tune=tune, draws=T - tune, z=z, philox_seed=seed, store_warmup=True,
-                                      mass="diag_adapt", mean0=self._mean0[None, :], var0=self._var0[None, :], eps0=eps0, **kw)
+                                      mass="diag_adapt", mean0=self._mean0[None, :], var0=self._var0[None, :], eps0=eps0, **kw,
+                                      **extra)
         self._base = self.iter_count
         self._served = q0.copy()
         brng.unpack_pcg64(states, [self.rng])  # the host generator continues where the device stopped
@@ -197,7 +203,21 @@ class B200NUTS:
 
     @property
     def sampling_state(self):
-        return {"iter_count": self.iter_count, "tune": self.tune, "divergences": self.divergences}
+        """What ``BaseHMC.sampling_state`` carries (hmc/base_hmc.py:61-71): counters, the step-size adaptation state
+        (``StepSizeState``, step_sizes.py:26-38) and the potential's state (``QuadPotentialDiagAdaptState`` with its two
+        ``WeightedVarianceState``, quadpotential.py:189-208, :396-403).  The chain runs ahead on the device, so the
+        adaptation state is the one at the END of the launched schedule (exported by the kernel, ``b200_chain_state``)."""
+        out = {"iter_count": self.iter_count, "tune": self.tune, "divergences": self.divergences}
+        st = getattr(self, "_state", None)
+        if st is not None and self._res is not None:
+            out["step_adapt"] = {"log_step": float(st.log_step[0]), "log_bar": float(st.log_bar[0]), "hbar": float(st.hbar[0]),
+                                 "count": int(st.da_count[0])}
+            out["potential"] = {"_var": st.var[0].copy(), "_n_samples": int(st.n_samples[0]),
+                                "adaptation_window": int(st.window[0]),
+                                "_foreground_var": {"n_samples": float(st.fg_n[0]), "mean": st.fg_mean[0].copy(), "raw_var": st.fg_m2[0].copy()},
+                                "_background_var": {"n_samples": float(st.bg_n[0]), "mean": st.bg_mean[0].copy(), "raw_var": st.bg_m2[0].copy()}}
+            out["launched_through_iteration"] = int(st.iter_count) + self._base
+        return out
 
 
 def from_pymc(model):

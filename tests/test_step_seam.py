@@ -119,3 +119,36 @@ def test_b200nuts_on_device_reproduces_golden_adaptive_prefix(golden):
     from pymc_b200 import engine
 
     _golden_prefix_through_step_seam(golden, engine.CompiledModel)
+
+
+@pytest.mark.gpu
+def test_b200nuts_sampling_state_and_changed_point_on_device(golden):
+    """sampling_state carries the step-size and potential state (hmc/base_hmc.py:61-71); a driver that changes the point
+    between calls gets a re-launch from ITS point, never stale draws."""
+    import warnings
+
+    from pymc_b200 import engine
+
+    spec = models.eight_schools()
+    s = B200NUTS(engine.CompiledModel(spec))
+    s.setup_chain(np.random.default_rng(3), 30, 10)
+    s.reset_tuning()
+    pt = {v.name: np.zeros(v.size) for v in spec.vars}
+    for i in range(5):
+        pt, st = s.step(pt)
+    state = s.sampling_state
+    assert state["iter_count"] == 5 and state["step_adapt"]["count"] >= 30 and state["launched_through_iteration"] == 40
+    assert state["potential"]["_var"].shape == (spec.n,) and np.all(state["potential"]["_var"] > 0)
+    assert state["potential"]["_foreground_var"]["mean"].shape == (spec.n,)
+    moved = {k: v + 0.25 for k, v in pt.items()}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pt2, st2 = s.step(moved)
+    assert any("re-launching" in str(x.message) for x in w)
+    assert s.iter_count == 6 and np.isfinite(st2[0]["energy"])
+    for i in range(6, 40):
+        if i == 30:
+            s.stop_tuning()
+        pt2, st2 = s.step(pt2)
+    with pytest.raises(RuntimeError):
+        s.step(pt2)

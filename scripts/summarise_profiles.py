@@ -14,7 +14,8 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__warps_eligible.avg.per_cycle_active", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
-        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_fp64.sum"]
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_fp64.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def raw_summary(name):
@@ -110,10 +111,14 @@ if __name__ == "__main__":
         json.dump({"kernel": "nuts_warp_kernel<RadonModel,6,1>", "launch": "2048 chains x (150 tune + 50 draws), scripts/ncu_target_radon.py",
                    "grad_evals_incl_start_state": evals, "dram_bytes_read": rd, "dram_bytes_write": wr,
                    "dram_bytes_per_grad_eval": (rd + wr) / evals, "algorithmic_bytes_per_grad_eval": 28180},
-                  open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+                  open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
     raw_summary("stochvol"); opcode_mix("stochvol")
     raw_summary("logistic"); opcode_mix("logistic")
     raw_summary("gemm"); opcode_mix("gemm")
+    raw_summary("logistic_tc"); opcode_mix("logistic_tc")
+    raw_summary("gemm_tc"); opcode_mix("gemm_tc")
+    launches(f"{tag}_launches_logistic_tc.csv", f"{tag}_launches_logistic_tc_summary.csv")
+    launches(f"{tag}_launches_mvgauss_tc.csv", f"{tag}_launches_mvgauss_tc_summary.csv")
     launches(f"{tag}_launches.csv", f"{tag}_launches_bench_summary.csv")
     launches(f"{tag}_launches_logistic.csv", f"{tag}_launches_logistic_summary.csv")
     launches(f"{tag}_launches_mvgauss.csv", f"{tag}_launches_mvgauss_summary.csv")

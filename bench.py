@@ -377,6 +377,26 @@ def make_roofline(workload, wl, per_launch, k_ms, fp64, dmma, peaks, traffic):
 # ---------------------------------------------------------------------------------------------
 # the CUDA engine arm
 # ---------------------------------------------------------------------------------------------
+def pcie_probe(dev, mib=512):
+    """Host link of THIS box: one pinned 512 MiB copy each way (CUDA events).  The e2e figure moves with it: the Radon step
+    sends 3 GB of draws to the host while the sampling half of the kernel runs."""
+    import torch
+
+    h = torch.empty(mib << 20, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(mib << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in {"h2d_GBps": (d, h), "d2h_GBps": (h, d)}.items():
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = (mib << 20) / (a.elapsed_time(b) * 1e-3) / 1e9
+    return out
+
+
 def b200_arm(args):
     import torch
 
@@ -500,6 +520,13 @@ def b200_arm(args):
             res_h = cm.nuts_run(q0_p, st_e, tune=tune, draws=draws, mean0=mean0_p, store_warmup=False,
                                 philox_seed=2000 + k, device_outputs=False, chain_offset=lo, pinned_outputs=True, **run_kw)
             ev_tot += int(res_h.summary["grad_evals"].sum()) - C * start_evals
+            if world > 1:
+                # the draws stay SHARDED: every rank's shard is already in its own pinned host buffer on this node (N PCIe
+                # links in parallel).  What rank 0 needs of the other ranks for the run's report -- the per-chain summaries
+                # (step size, tree statistics, evaluation counts) -- is gathered to rank 0 over NCCL here, inside the timed
+                # region.  The cost of gathering the DRAWS themselves to rank 0's HBM is measured separately below.
+                summ_all, _ = parallel.gather_chains(
+                    np.stack([np.asarray(v, dtype=np.float64) for v in res_h.summary.values()], axis=1), {}, chains_total, dst=0)
         torch.cuda.synchronize()
         dt = parallel.max_over_ranks(time.perf_counter() - t0)
         ev_all = parallel.sum_over_ranks(float(ev_tot))
@@ -507,6 +534,27 @@ def b200_arm(args):
         d2h = res_h.draws.nbytes + sum(v.nbytes for v in res_h.stats.values()) + sum(v.nbytes for v in res_h.summary.values()) + st_e.nbytes
         e2e = {"value": ev_all / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e}
+        if rank == 0:
+            e2e["host_link"] = pcie_probe(dev)
+        if world > 1:
+            e2e["gather"] = ("draws stay sharded: each rank copies its chains to its own pinned host buffer; per-chain "
+                             "summaries are gathered to rank 0 over NCCL inside the timed region")
+
+    # ---- N > 1: what gathering every rank's draws to rank 0 costs (NCCL gather over NVLink into rank 0's HBM) ---------
+    gather_info = None
+    if world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gd, _ = parallel.gather_chains(res.draws, {}, chains_total, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = parallel.max_over_ranks(g0.elapsed_time(g1))
+        nbytes = parallel.sum_over_ranks(float(res.draws.numel() * res.draws.element_size() if rank != 0 else 0))
+        gather_info = {"ms": g_ms, "bytes_to_rank0": nbytes, "GB_per_s": nbytes / (g_ms * 1e-3) / 1e9,
+                       "what": "dist.gather of the last step's device-resident draws to rank 0 (not part of value or e2e: "
+                               "the product leaves draws sharded unless sample_b200_nuts(gather='rank0') is asked for)"}
+        del gd
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------
     k_ms = float(np.mean(kernel_ms))
@@ -561,6 +609,7 @@ def b200_arm(args):
                        "momentum": "device philox", "l2": wl["l2"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "host_ms_between_launches": ms_total / args.steps - k_ms,
+            "gather_to_rank0": gather_info,
             "ess": {"min_bulk_ess_last_step": ess_min, "ess_per_sec": ess_min / step_s, "chains": C, "draws": draws},
             "grad_evals_incl_start_state": all_evals * world, "divergent_fraction": div_frac,
         }

@@ -120,6 +120,17 @@ struct b200_model {
         if (e == cudaSuccess) ls_arena_bytes = bytes;
         return e;
     }
+    void* stage_arena = nullptr;  // device staging of per-draw sampler statistics bound for host memory (kept between runs)
+    size_t stage_bytes = 0;
+    cudaError_t ensure_stage(size_t bytes) {
+        if (bytes <= stage_bytes) return cudaSuccess;
+        if (stage_arena) cudaFree(stage_arena);
+        stage_arena = nullptr;
+        stage_bytes = 0;
+        cudaError_t e = cudaMalloc(&stage_arena, bytes);
+        if (e == cudaSuccess) stage_bytes = bytes;
+        return e;
+    }
     cudaError_t ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return cudaSuccess;
         if (scratch) cudaFree(scratch);
@@ -131,6 +142,7 @@ struct b200_model {
     }
     ~b200_model() {
         if (ls_arena) cudaFree(ls_arena);
+        if (stage_arena) cudaFree(stage_arena);
         if (tc_a_hi) cudaFree(tc_a_hi);
         if (tc_a_lo) cudaFree(tc_a_lo);
         if (ir_scratch) cudaFree(ir_scratch);
@@ -630,10 +642,12 @@ struct Timer {
 // Host<->device staging of one array.
 struct Staged {
     DevBuf dev;
+    void* lent = nullptr;  // device staging lent by the caller (an arena in the model handle) instead of `dev`
     void* user = nullptr;
     size_t bytes = 0;
     bool host = false, out = false;
-    void* ptr() const { return host ? dev.p : user; }
+    void* dptr() const { return lent ? lent : dev.p; }
+    void* ptr() const { return host ? dptr() : user; }
 };
 // `direct`: an OUTPUT buffer in page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor) is
 // written by the kernel itself through its device alias (UVA), so the device->host transfer overlaps the run instead of
@@ -654,13 +668,13 @@ static int stage_in(Staged& s, const void* user, size_t bytes, int mem, bool cop
         cudaGetLastError();  // pageable memory: not an error, fall back to staging
     }
     if (s.host) {
-        CU(s.dev.alloc(bytes));
-        if (copy_in) CU(cudaMemcpyAsync(s.dev.p, user, bytes, cudaMemcpyHostToDevice, st));
+        if (!s.lent) CU(s.dev.alloc(bytes));
+        if (copy_in) CU(cudaMemcpyAsync(s.dptr(), user, bytes, cudaMemcpyHostToDevice, st));
     }
     return 0;
 }
 static int stage_out(Staged& s, cudaStream_t st) {
-    if (s.host && s.out) CU(cudaMemcpyAsync(s.user, s.dev.p, s.bytes, cudaMemcpyDeviceToHost, st));
+    if (s.host && s.out) CU(cudaMemcpyAsync(s.user, s.dptr(), s.bytes, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
@@ -822,6 +836,7 @@ static int gemm_nt(b200_model* m, cudaStream_t st, const double* Q, long long ld
 struct BatchScratch {  // logistic partial results
     DevBuf gpart, lpart;
     int gx = 0, cpad = 0;
+    long long cap_rows = 0;  // allocated gx * cpad (the product barely changes when the batch shrinks: more row CTAs per chain block)
 };
 
 
@@ -974,13 +989,14 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
     const int cb = (C + kLogiChains - 1) / kLogiChains;
     const long long n_slabs = (m->n_rows + kLogiRows - 1) / kLogiRows;
     const int gx = (int)std::max<long long>(1, std::min<long long>(n_slabs, 148 / std::min(cb, 148)));
-    if (!bs.gpart.p || bs.gx != gx || bs.cpad != cb * kLogiChains) {
-        bs.gx = gx;
-        bs.cpad = cb * kLogiChains;
+    bs.gx = gx;
+    bs.cpad = cb * kLogiChains;
+    if ((long long)gx * bs.cpad > bs.cap_rows) {
         if (bs.gpart.p) { cudaFree(bs.gpart.p); bs.gpart.p = nullptr; }
         if (bs.lpart.p) { cudaFree(bs.lpart.p); bs.lpart.p = nullptr; }
-        CU(bs.gpart.alloc((size_t)gx * bs.cpad * m->KP * sizeof(double)));
-        CU(bs.lpart.alloc((size_t)gx * bs.cpad * sizeof(double)));
+        bs.cap_rows = std::max<long long>((long long)gx * bs.cpad, 148LL * kLogiChains);
+        CU(bs.gpart.alloc((size_t)bs.cap_rows * m->KP * sizeof(double)));
+        CU(bs.lpart.alloc((size_t)bs.cap_rows * sizeof(double)));
     }
     int rc = 0;
     if (m->precision == B200_PRECISION_TC_FP16X2) {
@@ -1042,8 +1058,11 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_state = up((size_t)C * sizeof(LsState)), b_vecs = up((size_t)C * P.vec_stride * sizeof(double)), b_mat = up(mat);
     const size_t b_l = up((size_t)C * sizeof(double)), b_cnt = up(2 * sizeof(int)), b_mom = up((size_t)C * sizeof(int));
-    const int n_mats = dense ? 8 : 2;
-    CU(m->ensure_ls_arena(b_state + b_vecs + n_mats * b_mat + b_l + b_cnt + b_mom));
+    // compaction of the request rows once finished chains free a whole tile of them (lockstep.cuh: ls_compact_*)
+    const int ctile = std::max(1, env_int("B200_LS_COMPACT_TILE", 128));
+    const bool compact = env_int("B200_LS_COMPACT", 1) != 0 && C > ctile;
+    const int n_mats = (dense ? 8 : 2) + (compact ? 1 : 0);
+    CU(m->ensure_ls_arena(b_state + b_vecs + n_mats * b_mat + b_l + b_cnt + 3 * b_mom));
     char* a = static_cast<char*>(m->ls_arena);
     auto take = [&](size_t b) { char* p = a; a += b; return p; };
     P.state = reinterpret_cast<LsState*>(take(b_state));
@@ -1059,9 +1078,13 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
         P0b = reinterpret_cast<double*>(take(b_mat));
         V0b = reinterpret_cast<double*>(take(b_mat));
     }
+    double* Qalt = compact ? reinterpret_cast<double*>(take(b_mat)) : nullptr;
     P.logp_req = reinterpret_cast<double*>(take(b_l));
     P.counters = reinterpret_cast<int*>(take(b_cnt));
     P.mom_list = reinterpret_cast<int*>(take(b_mom));
+    P.slot = reinterpret_cast<int*>(take(b_mom));
+    int* new_slot = reinterpret_cast<int*>(take(b_mom));
+    if (!compact) P.slot = nullptr;
     // the padding columns of the request / result matrices must be zero (they are inside the GEMMs' k range) and the chain
     // vectors start from zero: clearing is bandwidth-trivial (2.6 GB at HBM speed = 0.4 ms), unlike allocating
     CU(cudaMemsetAsync(P.vecs, 0, b_vecs + n_mats * b_mat, st));
@@ -1075,11 +1098,12 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     CU(cudaGetLastError());
     ++launches;
     int n_mom = dense ? C : 0;  // every chain needs the momentum of draw 0
+    int C_eval = C;             // rows of the request matrices in use (shrinks when finished chains free a tile)
     for (;;) {
-        if (batch_eval(m, C, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
+        if (batch_eval(m, C_eval, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
         if (dense) {
             // w = Sigma g for every requested point (QuadPotentialFull.velocity, quadpotential.py:705-707)
-            if (gemm_nt(m, st, P.Greq, ld, C, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
+            if (gemm_nt(m, st, P.Greq, ld, C_eval, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
             ++launches;
             if (n_mom > 0) {
                 ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb);
@@ -1104,6 +1128,14 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
         CU(cudaStreamSynchronize(st));
         if (h[0] == 0) break;
         n_mom = dense ? h[1] : 0;
+        if (compact && (h[0] + ctile - 1) / ctile < (C_eval + ctile - 1) / ctile) {
+            ls_compact_slots_kernel<<<1, 1024, 0, st>>>(P, new_slot);
+            ls_compact_move_kernel<<<C, 256, 0, st>>>(P, new_slot, Qalt);
+            CU(cudaGetLastError());
+            std::swap(P.Qreq, Qalt);
+            C_eval = h[0];
+            launches += 2;
+        }
     }
     t.stop(launches);
     return 0;
@@ -1231,9 +1263,19 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     Staged st_arr[12], sm_arr[4];
     const size_t ct = (size_t)C * T;
     if (stats) {
+        // Sampler statistics are ONE 1-8 byte value per (chain, draw) and array: written straight into host memory they are
+        // 12 x C x T single-value PCIe write transactions (24 M for the Radon bench), which costs more link time than the
+        // draws themselves.  They are staged in HBM (one arena in the model handle) and leave with 12 DMA copies at the end
+        // (143 MB for the Radon bench).  The draws -- 256-byte coalesced row segments -- keep the direct path.
+        const bool direct_stats = getenv("B200_DIRECT_STATS") != nullptr;
+        if (mem == B200_MEM_HOST && !direct_stats) {
+            const size_t per = (ct * sizeof(double) + 255) & ~(size_t)255;
+            CU(m->ensure_stage(12 * per));
+            for (int i = 0; i < 12; ++i) st_arr[i].lent = static_cast<char*>(m->stage_arena) + i * per;
+        }
 #define B200_ST(i, field, type)                                                              \
     if (stats->field) {                                                                      \
-        if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st, /*direct=*/true)) return -1; \
+        if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st, /*direct=*/direct_stats)) return -1; \
         ds.field = (type*)st_arr[i].ptr();                                                   \
     }
         B200_ST(0, depth, int32_t) B200_ST(1, tree_size, int32_t) B200_ST(2, index_in_trajectory, int32_t)

@@ -76,6 +76,7 @@ struct LsDev {
     double* Qreq; double* Greq; double* Wreq;  // dense request / result matrices [C][ld], padding columns stay zero
     double* logp_req;                          // [C] (models that return logp from their own kernel)
     double* P0n; double* V0n;                  // prefetched momentum of the next draw [C][ld] (dense mass)
+    int* slot;                                 // [C] row of chain c in the request / result matrices (compaction; null: c)
     int* counters;                             // [0] active chains, [1] momentum requests
     int* mom_list;                             // [C] chains that requested momentum
     int logp_from_dot;                         // 1: logp = logp_const + 0.5 q.g  (Gaussian model)
@@ -99,9 +100,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     double* vb = P.vecs + (long long)chain * P.vec_stride;
     auto V = [&](int slot) -> double* { return vb + (long long)slot * n; };
     auto LVL = [&](int h, int which) -> double* { return vb + (long long)(LV_STACK + 8 * h + which) * n; };
-    double* qreq = P.Qreq + (long long)chain * P.ld;
-    const double* greq = P.Greq + (long long)chain * P.ld;
-    const double* wreq = P.dense ? P.Wreq + (long long)chain * P.ld : nullptr;
+    const int row = P.slot ? P.slot[chain] : chain;  // finished chains give their rows up (ls_compact_* below)
+    double* qreq = P.Qreq + (long long)row * P.ld;
+    const double* greq = P.Greq + (long long)row * P.ld;
+    const double* wreq = P.dense ? P.Wreq + (long long)row * P.ld : nullptr;
     const int Ttot = P.tune + P.draws, T_out = P.store_warmup ? Ttot : P.draws;
     Pcg64 rng;
     rng.load(S.rs_hi, S.rs_lo, S.ri_hi, S.ri_lo);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             for (int i = lane; i < n; i += TS) s = fma(qreq[i], greq[i], s);
             return P.logp_const + 0.5 * team_sum<W>(s, lane, red);
         }
-        return P.logp_req[chain];
+        return P.logp_req[row];
     };
 
     bool begin_draw = false, next_doubling = false, start_leapfrog = false, finish_draw = false, exhausted = false;
@@ -515,8 +517,50 @@ __global__ void __launch_bounds__(128) ls_init_kernel(const LsDev P) {
         const b200_pcg64 r = P.rng[chain];
         S.rs_hi = r.state_hi; S.rs_lo = r.state_lo; S.ri_hi = r.inc_hi; S.ri_lo = r.inc_lo;
         if (P.dense) { S.need_mom = 0; S.mom_it = 0; P.mom_list[chain] = chain; }
+        if (P.slot) P.slot[chain] = chain;
         P.state[chain] = S;
     }
+}
+
+// ---- compaction of the request rows -------------------------------------------------------------------------------------
+// Chains finish at different times (a few warm-up trees of depth 10 decide a chain's total), and the batched evaluation costs
+// the same for a finished chain's row as for a live one.  When enough chains have finished to free a whole tile of rows, the
+// live chains are renumbered to consecutive rows (in chain order) and the batch shrinks.  Two kernels: the new row of every
+// chain (one CTA, ballot scan), then the move of the pending request rows into the other request matrix.
+__global__ void __launch_bounds__(1024) ls_compact_slots_kernel(const LsDev P, int* new_slot) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < P.C; base += 1024) {
+        const int c = base + (int)threadIdx.x;
+        const int live = (c < P.C && P.state[c].phase != 2) ? 1 : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) warp_tot[w] = __popc(b);
+        __syncthreads();
+        int off = carry;
+        for (int j = 0; j < w; ++j) off += warp_tot[j];
+        if (c < P.C) new_slot[c] = live ? off + __popc(b & ((1u << lane) - 1u)) : -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int j = 0; j < 32; ++j) t += warp_tot[j];
+            carry += t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) ls_compact_move_kernel(const LsDev P, const int* new_slot, double* Qnew) {
+    const int chain = blockIdx.x;
+    const int ns = new_slot[chain];
+    if (ns < 0) return;
+    const double* src = P.Qreq + (long long)P.slot[chain] * P.ld;
+    double* dst = Qnew + (long long)ns * P.ld;
+    for (long long i = threadIdx.x; i < P.ld; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) P.slot[chain] = ns;
 }
 
 // z rows of the chains that asked for momentum -> dense batch Zb[m][ld]

@@ -200,3 +200,42 @@ def test_report_first_divergent_draw(golden, name):
                                              "teacher_forced_mismatches": forced[:20],
                                              "teacher_forced_identical_fraction": float(ok1.mean())})
     assert free_first == -1 or free_first >= 10
+
+
+def _lockstep_run(cm, C, *, tune, draws, mass, seed=11, **kw):
+    from pymc_b200 import rng as brng
+
+    spec = cm.spec
+    step_rngs, _, jit = brng.chain_generators(seed, C)
+    q0 = np.stack([spec.initial_point() + np.random.default_rng(s).uniform(-1, 1, spec.n) for s in jit])
+    return cm.nuts_run(q0, brng.pack_pcg64(step_rngs), tune=tune, draws=draws, mass=mass, store_warmup=True, philox_seed=5, **kw)
+
+
+@pytest.mark.parametrize("case", ["logistic_diag", "radon_dense"])
+def test_lockstep_row_compaction_changes_nothing(case, monkeypatch):
+    """Finished chains give their request rows up (lockstep.cuh: ls_compact_*): with a tile of 8 rows and 40 chains of
+    different lengths the batch shrinks several times during a short run; draws, statistics and evaluation counts must be
+    the ones of the run without compaction, bit for bit (same chain-block count => same reduction order)."""
+    from pymc_b200 import engine, models
+
+    if case == "logistic_diag":
+        cm = engine.CompiledModel(models.logistic(n_rows=4096, n_features=8, seed=2))
+        kw = dict(tune=25, draws=8, mass="diag_adapt")
+    else:
+        spec = models.radon(n_obs=200, n_counties=12, seed=4)
+        cm = engine.CompiledModel(spec)
+        A = np.random.default_rng(0).standard_normal((spec.n, spec.n)) * 0.05
+        cm.set_dense_mass(cov=np.eye(spec.n) * 0.05 + A @ A.T)
+        kw = dict(tune=20, draws=6, mass="dense")
+    monkeypatch.setenv("B200_LS_COMPACT", "0")
+    ref = _lockstep_run(cm, 40, **kw)
+    monkeypatch.setenv("B200_LS_COMPACT", "1")
+    monkeypatch.setenv("B200_LS_COMPACT_TILE", "8")
+    got = _lockstep_run(cm, 40, **kw)
+    ge = ref.summary["grad_evals"]
+    assert ge.max() > 1.2 * ge.min()  # chains do finish at different times
+    assert got.launches > ref.launches and (got.launches - ref.launches) % 2 == 0  # two kernels per compaction
+    np.testing.assert_array_equal(got.summary["grad_evals"], ge)
+    np.testing.assert_array_equal(got.draws, ref.draws)
+    for k in ref.stats:
+        np.testing.assert_array_equal(got.stats[k], ref.stats[k], err_msg=k)

@@ -516,10 +516,14 @@ def b200_arm(args):
         barrier()
         t0 = time.perf_counter()
         ev_tot = 0
+        call_ms, call_kernel_ms = [], []
         for k in range(n_e2e):
+            tc0 = time.perf_counter()
             res_h = cm.nuts_run(q0_p, st_e, tune=tune, draws=draws, mean0=mean0_p, store_warmup=False,
                                 philox_seed=2000 + k, device_outputs=False, chain_offset=lo, pinned_outputs=True, **run_kw)
             ev_tot += int(res_h.summary["grad_evals"].sum()) - C * start_evals
+            call_ms.append(1e3 * (time.perf_counter() - tc0))
+            call_kernel_ms.append(res_h.kernel_ms)
             if world > 1:
                 # the draws stay SHARDED: every rank's shard is already in its own pinned host buffer on this node (N PCIe
                 # links in parallel).  What rank 0 needs of the other ranks for the run's report -- the per-chain summaries
@@ -533,7 +537,9 @@ def b200_arm(args):
         h2d = q0_p.nbytes + (mean0_p.nbytes if mean0_p is not None else 0) + st_e.nbytes
         d2h = res_h.draws.nbytes + sum(v.nbytes for v in res_h.stats.values()) + sum(v.nbytes for v in res_h.summary.values()) + st_e.nbytes
         e2e = {"value": ev_all / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e}
+               "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               # this rank's calls: wall time of each public-API call and the kernel time inside it (CUDA events)
+               "call_ms": call_ms, "call_kernel_ms": call_kernel_ms}
         if rank == 0:
             e2e["host_link"] = pcie_probe(dev)
         if world > 1:

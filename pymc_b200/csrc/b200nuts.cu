@@ -11,6 +11,7 @@
 #include <numeric>
 #include <string>
 #include <type_traits>
+#include <chrono>
 #include <vector>
 
 #include "dense.cuh"
@@ -1236,6 +1237,12 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     if (cfg->adaptation_window < 1) return fail("b200_nuts_run: adaptation_window must be >= 1");
     CU(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // B200_TRACE=1: host-side wall time of the call's phases on stderr (staging | run | copy-out)
+    const bool trace = getenv("B200_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
 
     // iterations of this call: [it0, it0 + n_iter) of the chain's tune + draws schedule (default: all of it)
     const long long Tsched = (long long)cfg->tune + cfg->draws;
@@ -1348,6 +1355,8 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         P.tr_kind = m->tr_kind; P.tr_lo = m->tr_lo; P.tr_hi = m->tr_hi;
     }
 
+    const double tr_stage = trace ? since(tr0) : 0.0;
+    const auto tr1 = std::chrono::steady_clock::now();
     if (lockstep) {
         LsDev Q{};
         Q.C = C; Q.n = n; Q.tune = P.tune; Q.draws = P.draws; Q.max_td = P.max_td; Q.early_td = P.early_td;
@@ -1365,11 +1374,16 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         if (dispatch(m, L)) return -1;
     }
 
+    const double tr_run = trace ? since(tr1) : 0.0;
+    const auto tr2 = std::chrono::steady_clock::now();
     if (stage_out(s_rng, st) || stage_out(s_draws, st)) return -1;
     for (auto& s : st_arr) if (stage_out(s, st)) return -1;
     for (auto& s : sm_arr) if (stage_out(s, st)) return -1;
     for (auto& s : st_state) if (stage_out(s, st)) return -1;
     CU(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "[b200_nuts_run] staging %.2f ms | run %.2f ms (kernels %.2f ms) | copy-out %.2f ms | mem=%s\n", tr_stage, tr_run,
+                g_last_ms, since(tr2), mem == B200_MEM_HOST ? "host" : "device");
     return 0;
 }
 

@@ -36,6 +36,21 @@ constexpr int kLsLevels = 12;
 #define B200_LS_UNROLL_(n) B200_LS_PRAGMA(unroll n)
 #define B200_LS_UNROLL B200_LS_UNROLL_(B200_LS_UNROLL_N)
 
+// A pass over a chain's vectors in tiles of U elements per thread: ALL loads of a tile, then the arithmetic and the stores.
+// Written as `for (i) { load; store; }` the compiler must keep every load behind the previous iteration's store (the vectors
+// are slots of one allocation, so it cannot rule out aliasing), and the pass runs one DRAM latency per element: measured
+// 1.3 TB/s for ls_advance_kernel<16> at n = 10^4 (profiles/r2_tc_launches_mvgauss_tc_summary.csv).  Element order per thread is
+// unchanged (i = lane, lane + TS, ...), so every per-thread partial sum keeps its bits.
+template <int U, int TS, class Load, class Store>
+__device__ __forceinline__ void ls_tiled(int lane, int n, Load&& load, Store&& store) {
+    for (int i0 = lane; i0 < n; i0 += TS * U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * TS; if (i < n) load(u, i); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * TS; if (i < n) store(u, i); }
+    }
+}
+
 struct LsState {  // per-chain scalars, resident in HBM between calls
     int phase;    // 0 = INIT (waiting for the evaluation at q0), 1 = LEAF (waiting for a leapfrog's evaluation), 2 = DONE
     int it, d_iter, maxd, depth, leaf, n_leaf, dir, w_idx, L_idx, R_idx, n_prop, m_pidx, c_pidx;
@@ -87,7 +102,7 @@ struct LsDev {
 // thread of the team (common.cuh), so every thread carries an identical private copy of the scalar state.
 template <int W>
 __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const LsDev P) {
-    constexpr int TS = 32 * W;
+    constexpr int TS = 32 * W, U = B200_LS_UNROLL_N;
     __shared__ double red_s[W == 1 ? 1 : 8 * W];
     double* red = red_s;
     const int lane = (W == 1) ? (threadIdx.x & 31) : (int)threadIdx.x;  // index inside the team
@@ -141,16 +156,20 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         {
             double* p = V(LV_P); double* v = V(LV_V); double* q = V(LV_Q); double* g = V(LV_G); double* w = V(LV_W);
             const double* var = V(LV_VAR);
-            B200_LS_UNROLL
-            for (int i = lane; i < n; i += TS) {
-                const double gi = greq[i];
-                const double pi = fma(dt, gi, p[i]);
-                double vi;
-                if (dense) { const double wi = wreq[i]; vi = fma(dt, wi, v[i]); w[i] = wi; }
-                else vi = var[i] * pi;
-                p[i] = pi; v[i] = vi; g[i] = gi; q[i] = qreq[i];
-                kk = fma(pi, vi, kk);
-            }
+            double g_[U], p_[U], q_[U], w_[U], v_[U];
+            ls_tiled<U, TS>(lane, n,
+                [&](int u, int i) {
+                    g_[u] = greq[i]; p_[u] = p[i]; q_[u] = qreq[i];
+                    if (dense) { w_[u] = wreq[i]; v_[u] = v[i]; } else v_[u] = var[i];
+                },
+                [&](int u, int i) {
+                    const double pi = fma(dt, g_[u], p_[u]);
+                    double vi;
+                    if (dense) { vi = fma(dt, w_[u], v_[u]); w[i] = w_[u]; }
+                    else vi = v_[u] * pi;
+                    p[i] = pi; v[i] = vi; g[i] = g_[u]; q[i] = q_[u];
+                    kk = fma(pi, vi, kk);
+                });
         }
         const double E = 0.5 * team_sum<W>(kk, lane, red) - logp;
         ++S.n_grad;
@@ -166,12 +185,18 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             sub_div = true;
         } else {
             // the leaf as a height-0 subtree
-            B200_LS_UNROLL
-            for (int i = lane; i < n; i += TS) {
-                const double pi = V(LV_P)[i];
-                V(LV_CLP)[i] = pi; V(LV_CPS)[i] = pi; V(LV_CLV)[i] = V(LV_V)[i];
-                V(LV_CPQ)[i] = V(LV_Q)[i]; V(LV_CPQG)[i] = V(LV_G)[i];
-                if (dense) V(LV_CPQW)[i] = V(LV_W)[i];
+            {
+                double p_[U], v_[U], q_[U], g_[U], w_[U];
+                ls_tiled<U, TS>(lane, n,
+                    [&](int u, int i) {
+                        p_[u] = V(LV_P)[i]; v_[u] = V(LV_V)[i]; q_[u] = V(LV_Q)[i]; g_[u] = V(LV_G)[i];
+                        if (dense) w_[u] = V(LV_W)[i];
+                    },
+                    [&](int u, int i) {
+                        V(LV_CLP)[i] = p_[u]; V(LV_CPS)[i] = p_[u]; V(LV_CLV)[i] = v_[u];
+                        V(LV_CPQ)[i] = q_[u]; V(LV_CPQG)[i] = g_[u];
+                        if (dense) V(LV_CPQW)[i] = w_[u];
+                    });
             }
             S.c_logw = -dE; S.c_pe = E; S.c_plogp = logp; S.c_pidx = S.w_idx;
             // ---- merges while the binary counter carries (nuts.py:452-476) -------------------------------
@@ -183,20 +208,25 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 double* c_lp = V(LV_CLP); double* c_lv = V(LV_CLV); double* c_ps = V(LV_CPS);
                 const double* wp = V(LV_P); const double* wv = V(LV_V);
                 double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                B200_LS_UNROLL
-                for (int i = lane; i < n; i += TS) {
-                    const double tl = t_lp[i], tlv = t_lv[i], tr = t_rp[i], trv = t_rv[i], tp = t_ps[i];
-                    const double cl = c_lp[i], clv = c_lv[i], cp = c_ps[i];
-                    const double s = tp + cp, vr = wv[i];
-                    dots[0] = fma(s, tlv, dots[0]);
-                    dots[1] = fma(s, vr, dots[1]);
-                    const double s1 = tp + cl;
-                    dots[2] = fma(s1, tlv, dots[2]);
-                    dots[3] = fma(s1, clv, dots[3]);
-                    const double s2 = tr + cp;
-                    dots[4] = fma(s2, trv, dots[4]);
-                    dots[5] = fma(s2, vr, dots[5]);
-                    c_lp[i] = tl; c_lv[i] = tlv; c_ps[i] = s;
+                {
+                    double tl_[U], tlv_[U], tr_[U], trv_[U], tp_[U], cl_[U], clv_[U], cp_[U], vr_[U];
+                    ls_tiled<U, TS>(lane, n,
+                        [&](int u, int i) {
+                            tl_[u] = t_lp[i]; tlv_[u] = t_lv[i]; tr_[u] = t_rp[i]; trv_[u] = t_rv[i]; tp_[u] = t_ps[i];
+                            cl_[u] = c_lp[i]; clv_[u] = c_lv[i]; cp_[u] = c_ps[i]; vr_[u] = wv[i];
+                        },
+                        [&](int u, int i) {
+                            const double s = tp_[u] + cp_[u];
+                            dots[0] = fma(s, tlv_[u], dots[0]);
+                            dots[1] = fma(s, vr_[u], dots[1]);
+                            const double s1 = tp_[u] + cl_[u];
+                            dots[2] = fma(s1, tlv_[u], dots[2]);
+                            dots[3] = fma(s1, clv_[u], dots[3]);
+                            const double s2 = tr_[u] + cp_[u];
+                            dots[4] = fma(s2, trv_[u], dots[4]);
+                            dots[5] = fma(s2, vr_[u], dots[5]);
+                            c_lp[i] = tl_[u]; c_lv[i] = tlv_[u]; c_ps[i] = s;
+                        });
                     (void)wp;
                 }
                 team_sum_n<W>(dots, lane, red);
@@ -210,11 +240,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 const double u = rng.next_double();
                 if (!(u * (1.0 + e_w) < (dlw >= 0.0 ? 1.0 : e_w))) {  // keep tree1's proposal
                     const double* t_pq = LVL(h, 5); const double* t_pqg = LVL(h, 6); const double* t_pqw = LVL(h, 7);
-                    B200_LS_UNROLL
-                    for (int i = lane; i < n; i += TS) {
-                        V(LV_CPQ)[i] = t_pq[i]; V(LV_CPQG)[i] = t_pqg[i];
-                        if (dense) V(LV_CPQW)[i] = t_pqw[i];
-                    }
+                    double a_[U], b_[U], c_[U];
+                    ls_tiled<U, TS>(lane, n,
+                        [&](int u, int i) { a_[u] = t_pq[i]; b_[u] = t_pqg[i]; if (dense) c_[u] = t_pqw[i]; },
+                        [&](int u, int i) { V(LV_CPQ)[i] = a_[u]; V(LV_CPQG)[i] = b_[u]; if (dense) V(LV_CPQW)[i] = c_[u]; });
                     S.c_pe = S.sc_pe[h]; S.c_plogp = S.sc_plogp[h]; S.c_pidx = S.sc_pidx[h];
                 }
                 S.c_logw = logw;
@@ -222,13 +251,18 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             }
             if (!sub_turn && S.leaf + 1 < S.n_leaf) {
                 // park the finished subtree (height h) until its right sibling is built
-                B200_LS_UNROLL
-                for (int i = lane; i < n; i += TS) {
-                    LVL(h, 0)[i] = V(LV_CLP)[i]; LVL(h, 1)[i] = V(LV_CLV)[i];
-                    LVL(h, 2)[i] = V(LV_P)[i];   LVL(h, 3)[i] = V(LV_V)[i];
-                    LVL(h, 4)[i] = V(LV_CPS)[i]; LVL(h, 5)[i] = V(LV_CPQ)[i]; LVL(h, 6)[i] = V(LV_CPQG)[i];
-                    if (dense) LVL(h, 7)[i] = V(LV_CPQW)[i];
-                }
+                double r_[8][U];
+                ls_tiled<U, TS>(lane, n,
+                    [&](int u, int i) {
+                        r_[0][u] = V(LV_CLP)[i]; r_[1][u] = V(LV_CLV)[i]; r_[2][u] = V(LV_P)[i]; r_[3][u] = V(LV_V)[i];
+                        r_[4][u] = V(LV_CPS)[i]; r_[5][u] = V(LV_CPQ)[i]; r_[6][u] = V(LV_CPQG)[i];
+                        if (dense) r_[7][u] = V(LV_CPQW)[i];
+                    },
+                    [&](int u, int i) {
+                        LVL(h, 0)[i] = r_[0][u]; LVL(h, 1)[i] = r_[1][u]; LVL(h, 2)[i] = r_[2][u]; LVL(h, 3)[i] = r_[3][u];
+                        LVL(h, 4)[i] = r_[4][u]; LVL(h, 5)[i] = r_[5][u]; LVL(h, 6)[i] = r_[6][u];
+                        if (dense) LVL(h, 7)[i] = r_[7][u];
+                    });
                 S.sc_logw[h] = S.c_logw; S.sc_pe[h] = S.c_pe; S.sc_plogp[h] = S.c_plogp; S.sc_pidx[h] = S.c_pidx;
             }
         }
@@ -246,12 +280,16 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                 // new outer edge = integrator state
                 {
                     const int b = dir > 0 ? LV_RQ : LV_LQ;
-                    B200_LS_UNROLL
-                    for (int i = lane; i < n; i += TS) {
-                        V(b + 0)[i] = V(LV_Q)[i]; V(b + 1)[i] = V(LV_P)[i]; V(b + 2)[i] = V(LV_G)[i];
-                        V(b + 3)[i] = V(LV_V)[i];
-                        if (dense) V(b + 4)[i] = V(LV_W)[i];
-                    }
+                    double r_[5][U];
+                    ls_tiled<U, TS>(lane, n,
+                        [&](int u, int i) {
+                            r_[0][u] = V(LV_Q)[i]; r_[1][u] = V(LV_P)[i]; r_[2][u] = V(LV_G)[i]; r_[3][u] = V(LV_V)[i];
+                            if (dense) r_[4][u] = V(LV_W)[i];
+                        },
+                        [&](int u, int i) {
+                            V(b + 0)[i] = r_[0][u]; V(b + 1)[i] = r_[1][u]; V(b + 2)[i] = r_[2][u]; V(b + 3)[i] = r_[3][u];
+                            if (dense) V(b + 4)[i] = r_[4][u];
+                        });
                     if (dir > 0) S.R_idx = S.w_idx; else S.L_idx = S.w_idx;
                 }
                 // biased progressive pick (nuts.py:370-374)
@@ -260,11 +298,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                     const double dlw = S.c_logw - S.m_logw;
                     const double e_w = exp(-fabs(dlw));
                     if (dlw >= 0.0 || u < e_w) {
-                        B200_LS_UNROLL
-                        for (int i = lane; i < n; i += TS) {
-                            V(LV_PQ)[i] = V(LV_CPQ)[i]; V(LV_PQG)[i] = V(LV_CPQG)[i];
-                            if (dense) V(LV_PQW)[i] = V(LV_CPQW)[i];
-                        }
+                        double a_[U], b_[U], c_[U];
+                        ls_tiled<U, TS>(lane, n,
+                            [&](int u, int i) { a_[u] = V(LV_CPQ)[i]; b_[u] = V(LV_CPQG)[i]; if (dense) c_[u] = V(LV_CPQW)[i]; },
+                            [&](int u, int i) { V(LV_PQ)[i] = a_[u]; V(LV_PQG)[i] = b_[u]; if (dense) V(LV_PQW)[i] = c_[u]; });
                         S.m_pe = S.c_pe; S.m_plogp = S.c_plogp; S.m_pidx = S.c_pidx;
                     }
                     S.m_logw = (dlw == 0.0) ? S.c_logw + 0.69314718055994530942
@@ -278,20 +315,25 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
                     const double* cps = V(LV_CPS); const double* clp = V(LV_CLP); const double* clv = V(LV_CLV);
                     const double* wv = V(LV_V);
                     double dots[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    B200_LS_UNROLL
-                    for (int i = lane; i < n; i += TS) {
-                        const double so = PS[i], cp = cps[i];
-                        const double s = so + cp;
-                        PS[i] = s;
-                        const double vf = farv[i], vw = wv[i];
-                        dots[0] = fma(s, vf, dots[0]);
-                        dots[1] = fma(s, vw, dots[1]);
-                        const double a = so + clp[i];
-                        dots[2] = fma(a, vf, dots[2]);
-                        dots[3] = fma(a, clv[i], dots[3]);
-                        const double b = nearp[i] + cp;
-                        dots[4] = fma(b, nearv[i], dots[4]);
-                        dots[5] = fma(b, vw, dots[5]);
+                    {
+                        double so_[U], cp_[U], vf_[U], vw_[U], cl_[U], clv_[U], np_[U], nv_[U];
+                        ls_tiled<U, TS>(lane, n,
+                            [&](int u, int i) {
+                                so_[u] = PS[i]; cp_[u] = cps[i]; vf_[u] = farv[i]; vw_[u] = wv[i];
+                                cl_[u] = clp[i]; clv_[u] = clv[i]; np_[u] = nearp[i]; nv_[u] = nearv[i];
+                            },
+                            [&](int u, int i) {
+                                const double s = so_[u] + cp_[u];
+                                PS[i] = s;
+                                dots[0] = fma(s, vf_[u], dots[0]);
+                                dots[1] = fma(s, vw_[u], dots[1]);
+                                const double a = so_[u] + cl_[u];
+                                dots[2] = fma(a, vf_[u], dots[2]);
+                                dots[3] = fma(a, clv_[u], dots[3]);
+                                const double b = np_[u] + cp_[u];
+                                dots[4] = fma(b, nv_[u], dots[4]);
+                                dots[5] = fma(b, vw_[u], dots[5]);
+                            });
                         (void)farp;
                     }
                     team_sum_n<W>(dots, lane, red);
@@ -314,12 +356,15 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         const bool rec = P.store_warmup || !tuning;
         const int t_out = P.store_warmup ? S.it : S.it - P.tune;
         // accepted position (+ its gradient, Sigma.gradient and logp) becomes the chain state
-        B200_LS_UNROLL
-        for (int i = lane; i < n; i += TS) {
-            const double qi = V(LV_PQ)[i];
-            V(LV_Q)[i] = qi; V(LV_G)[i] = V(LV_PQG)[i];
-            if (dense) V(LV_W)[i] = V(LV_PQW)[i];
-            if (rec) P.draws_out[((long long)chain * T_out + t_out) * n + i] = constrained(qi, i, P.tr_kind, P.tr_lo, P.tr_hi);
+        {
+            double a_[U], b_[U], c_[U];
+            ls_tiled<U, TS>(lane, n,
+                [&](int u, int i) { a_[u] = V(LV_PQ)[i]; b_[u] = V(LV_PQG)[i]; if (dense) c_[u] = V(LV_PQW)[i]; },
+                [&](int u, int i) {
+                    V(LV_Q)[i] = a_[u]; V(LV_G)[i] = b_[u];
+                    if (dense) V(LV_W)[i] = c_[u];
+                    if (rec) P.draws_out[((long long)chain * T_out + t_out) * n + i] = constrained(a_[u], i, P.tr_kind, P.tr_lo, P.tr_hi);
+                });
         }
         S.cur_logp = S.m_plogp;
         if (adapting) {  // step_sizes.py:66-78
@@ -334,21 +379,24 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             if (S.k_samples > P.discard) {
                 S.fg_n += 1.0; S.bg_n += 1.0;
                 double* fm = V(S.fg_m); double* fv = V(S.fg_v); double* bm = V(S.bg_m); double* bv = V(S.bg_v);
-                B200_LS_UNROLL
-                for (int i = lane; i < n; i += TS) {
-                    const double x = V(LV_Q)[i];
-                    double mean = fm[i], d0 = x - mean;
-                    mean = __dadd_rn(mean, d0 / S.fg_n); fm[i] = mean;
-                    fv[i] = __dadd_rn(fv[i], __dmul_rn(d0, x - mean));
-                    mean = bm[i]; d0 = x - mean;
-                    mean = __dadd_rn(mean, d0 / S.bg_n); bm[i] = mean;
-                    bv[i] = __dadd_rn(bv[i], __dmul_rn(d0, x - mean));
-                }
+                double x_[U], fm_[U], fv_[U], bm_[U], bv_[U];
+                ls_tiled<U, TS>(lane, n,
+                    [&](int u, int i) { x_[u] = V(LV_Q)[i]; fm_[u] = fm[i]; fv_[u] = fv[i]; bm_[u] = bm[i]; bv_[u] = bv[i]; },
+                    [&](int u, int i) {
+                        const double x = x_[u];
+                        double mean = fm_[u], d0 = x - mean;
+                        mean = __dadd_rn(mean, d0 / S.fg_n); fm[i] = mean;
+                        fv[i] = __dadd_rn(fv_[u], __dmul_rn(d0, x - mean));
+                        mean = bm_[u]; d0 = x - mean;
+                        mean = __dadd_rn(mean, d0 / S.bg_n); bm[i] = mean;
+                        bv[i] = __dadd_rn(bv_[u], __dmul_rn(d0, x - mean));
+                    });
             }
             if (S.k_samples > S.window) {
                 const double* fv = V(S.fg_v);
-                B200_LS_UNROLL
-                for (int i = lane; i < n; i += TS) V(LV_VAR)[i] = fmin(fmax(fv[i] / S.fg_n, 1e-12), 1e12);
+                double f_[U];
+                ls_tiled<U, TS>(lane, n, [&](int u, int i) { f_[u] = fv[i]; },
+                                [&](int u, int i) { V(LV_VAR)[i] = fmin(fmax(f_[u] / S.fg_n, 1e-12), 1e12); });
             }
             if (S.k_samples > 0 && S.k_samples % S.window == 0) {
                 const int tm = S.fg_m, tv = S.fg_v;
@@ -389,8 +437,9 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             double* p = V(LV_P); double* v = V(LV_V);
             if (dense) {
                 const double* p0 = P.P0n + (long long)chain * P.ld; const double* v0 = P.V0n + (long long)chain * P.ld;
-                B200_LS_UNROLL
-                for (int i = lane; i < n; i += TS) { const double pi = p0[i], vi = v0[i]; p[i] = pi; v[i] = vi; kin = fma(pi, vi, kin); }
+                double a_[U], b_[U];
+                ls_tiled<U, TS>(lane, n, [&](int u, int i) { a_[u] = p0[i]; b_[u] = v0[i]; },
+                                [&](int u, int i) { p[i] = a_[u]; v[i] = b_[u]; kin = fma(a_[u], b_[u], kin); });
             } else {
                 const double* var = V(LV_VAR);
                 B200_LS_UNROLL
@@ -417,14 +466,21 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         } else {
             S.eps = exp(adapting ? S.log_step : S.log_bar);
             S.maxd = (tuning && S.it < 200) ? P.early_td : P.max_td;
-            B200_LS_UNROLL
-            for (int i = lane; i < n; i += TS) {
-                const double qi = V(LV_Q)[i], pi = V(LV_P)[i], gi = V(LV_G)[i], vi = V(LV_V)[i];
-                V(LV_LQ)[i] = qi; V(LV_RQ)[i] = qi; V(LV_PQ)[i] = qi;
-                V(LV_LP)[i] = pi; V(LV_RP)[i] = pi; V(LV_PS)[i] = pi;
-                V(LV_LG)[i] = gi; V(LV_RG)[i] = gi; V(LV_PQG)[i] = gi;
-                V(LV_LV)[i] = vi; V(LV_RV)[i] = vi;
-                if (dense) { const double wi = V(LV_W)[i]; V(LV_LW)[i] = wi; V(LV_RW)[i] = wi; V(LV_PQW)[i] = wi; }
+            {
+                double q_[U], p_[U], g_[U], v_[U], w_[U];
+                ls_tiled<U, TS>(lane, n,
+                    [&](int u, int i) {
+                        q_[u] = V(LV_Q)[i]; p_[u] = V(LV_P)[i]; g_[u] = V(LV_G)[i]; v_[u] = V(LV_V)[i];
+                        if (dense) w_[u] = V(LV_W)[i];
+                    },
+                    [&](int u, int i) {
+                        const double qi = q_[u], pi = p_[u], gi = g_[u], vi = v_[u];
+                        V(LV_LQ)[i] = qi; V(LV_RQ)[i] = qi; V(LV_PQ)[i] = qi;
+                        V(LV_LP)[i] = pi; V(LV_RP)[i] = pi; V(LV_PS)[i] = pi;
+                        V(LV_LG)[i] = gi; V(LV_RG)[i] = gi; V(LV_PQG)[i] = gi;
+                        V(LV_LV)[i] = vi; V(LV_RV)[i] = vi;
+                        if (dense) { const double wi = w_[u]; V(LV_LW)[i] = wi; V(LV_RW)[i] = wi; V(LV_PQW)[i] = wi; }
+                    });
             }
             S.L_idx = S.R_idx = 0;
             S.m_logw = 0.0; S.m_pe = S.E0; S.m_plogp = S.cur_logp; S.m_pidx = 0;
@@ -438,13 +494,18 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         team_sync<W>();
         S.dir = (rng.next_double() < 0.5) ? 1 : -1;  // nuts.py:215
         const int b = S.dir > 0 ? LV_RQ : LV_LQ;
-        B200_LS_UNROLL
-        for (int i = lane; i < n; i += TS) {
-            V(LV_Q)[i] = V(b + 0)[i];
-            const double pi = V(b + 1)[i], vi = V(b + 3)[i];
-            V(LV_P)[i] = pi; V(LV_G)[i] = V(b + 2)[i]; V(LV_V)[i] = vi;
-            if (dense) V(LV_W)[i] = V(b + 4)[i];
-            V(LV_NEARP)[i] = pi; V(LV_NEARV)[i] = vi;
+        {
+            double r_[5][U];
+            ls_tiled<U, TS>(lane, n,
+                [&](int u, int i) {
+                    r_[0][u] = V(b + 0)[i]; r_[1][u] = V(b + 1)[i]; r_[2][u] = V(b + 2)[i]; r_[3][u] = V(b + 3)[i];
+                    if (dense) r_[4][u] = V(b + 4)[i];
+                },
+                [&](int u, int i) {
+                    V(LV_Q)[i] = r_[0][u]; V(LV_P)[i] = r_[1][u]; V(LV_G)[i] = r_[2][u]; V(LV_V)[i] = r_[3][u];
+                    if (dense) V(LV_W)[i] = r_[4][u];
+                    V(LV_NEARP)[i] = r_[1][u]; V(LV_NEARV)[i] = r_[3][u];
+                });
         }
         S.w_idx = S.dir > 0 ? S.R_idx : S.L_idx;
         S.leaf = 0;
@@ -458,13 +519,18 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         const double es = S.dir * S.eps, dt = 0.5 * es;
         double* p = V(LV_P); double* v = V(LV_V);
         const double* q = V(LV_Q); const double* g = V(LV_G); const double* w = V(LV_W); const double* var = V(LV_VAR);
-        B200_LS_UNROLL
-        for (int i = lane; i < n; i += TS) {
-            const double pi = fma(dt, g[i], p[i]);
-            const double vi = dense ? fma(dt, w[i], v[i]) : var[i] * pi;
-            p[i] = pi; v[i] = vi;
-            qreq[i] = fma(es, vi, q[i]);
-        }
+        double g_[U], p_[U], q_[U], w_[U], v_[U];
+        ls_tiled<U, TS>(lane, n,
+            [&](int u, int i) {
+                g_[u] = g[i]; p_[u] = p[i]; q_[u] = q[i];
+                if (dense) { w_[u] = w[i]; v_[u] = v[i]; } else v_[u] = var[i];
+            },
+            [&](int u, int i) {
+                const double pi = fma(dt, g_[u], p_[u]);
+                const double vi = dense ? fma(dt, w_[u], v_[u]) : v_[u] * pi;
+                p[i] = pi; v[i] = vi;
+                qreq[i] = fma(es, vi, q_[u]);
+            });
         S.phase = 1;
     }
 

@@ -501,7 +501,9 @@ def b200_arm(args):
 
     # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region --------------
     e2e = None
+    near = parallel.near_gpu(local)
     if not args.no_e2e:
+        near.__enter__()  # pinned buffers are allocated on the GPU's NUMA node (restored before the CPU arm runs)
         T = draws
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
         q0_p = pin((C, n), torch.float64); q0_p[:] = q0_host
@@ -542,6 +544,8 @@ def b200_arm(args):
                "call_ms": call_ms, "call_kernel_ms": call_kernel_ms}
         if rank == 0:
             e2e["host_link"] = pcie_probe(dev)
+            e2e["host_numa"] = near.info
+        near.__exit__()
         if world > 1:
             e2e["gather"] = ("draws stay sharded: each rank copies its chains to its own pinned host buffer; per-chain "
                              "summaries are gathered to rank 0 over NCCL inside the timed region")

@@ -70,6 +70,7 @@ class CompiledModel:
         _lib.require_gpu()
         if device is not None:
             _lib.check(self._lib.b200_set_device(device))
+        self.device = 0 if device is None else int(device)
         d = _lib.ModelDesc()
         d.kind, d.n = spec.kind, spec.n
         keep = []
@@ -325,8 +326,13 @@ class CompiledModel:
             eps0_b = None if eps0 is None else np.broadcast_to(_f64(eps0), (Cn,)).copy()
             rng_b = rng_states
             if pinned_outputs:
-                mk = lambda shape, dt: pooled(lambda: torch.empty(tuple(shape), dtype=tdt[dt], pin_memory=True).numpy(),  # noqa: E731
-                                              shape, dt, "pin")
+                def pinned(shape, dt):  # page-locked memory on the GPU's own NUMA node (parallel.near_gpu)
+                    from . import parallel
+
+                    with parallel.near_gpu(self.device):
+                        return torch.empty(tuple(shape), dtype=tdt[dt], pin_memory=True).numpy()
+
+                mk = lambda shape, dt: pooled(lambda: pinned(shape, dt), shape, dt, "pin")  # noqa: E731
             else:
                 mk = lambda shape, dt: np.empty(shape, dtype=dt)  # noqa: E731
         draws_b = mk((Cn, T, self.n), np.float64)

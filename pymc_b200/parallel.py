@@ -164,3 +164,66 @@ def pooled_warmup_run(cm, q0, rng_states, *, tune, draws, mean0=None, window=101
     res = cm.nuts_run(q0, rng_states, mean0=mean0, store_warmup=False, iter_begin=begin, iter_count=tune + draws - begin,
                       resume=state, **common)
     return res
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Host memory next to the GPU.  The sampling kernel writes draws straight into page-locked host memory (b200nuts.cu:
+# stage_in, `direct`); on a two-socket box those writes cross the inter-socket link when the buffer was allocated on the
+# other socket, and the kernel then runs at the speed of that link.  Page-locked allocations follow the allocating thread's
+# NUMA policy, so binding the thread to the CPUs of the GPU's node WHILE the buffers are allocated is enough.
+# ------------------------------------------------------------------------------------------------------------------------
+def gpu_numa_cpus(device: int) -> tuple[int, set[int]]:
+    """(NUMA node of the GPU or -1, the CPUs local to it -- empty when the platform does not say)."""
+    import torch
+
+    pr = torch.cuda.get_device_properties(device)
+    try:
+        dom, bus, dev = int(getattr(pr, "pci_domain_id", 0)), int(pr.pci_bus_id), int(pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus: set[int] = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except (OSError, ValueError, AttributeError):
+        return -1, set()
+
+
+class near_gpu:
+    """``with near_gpu(device): allocate pinned buffers`` -- restricts the calling thread to the GPU-local CPUs for the
+    duration (restored on exit); a no-op where the platform reports no locality or the local CPUs are outside the cgroup."""
+
+    def __init__(self, device: int):
+        self.device, self.saved, self.info = device, None, {"numa_node": -1, "bound": False}
+
+    def __enter__(self):
+        import os
+
+        if os.environ.get("B200_NO_NUMA_BIND"):
+            return self
+        node, cpus = gpu_numa_cpus(self.device)
+        self.info["numa_node"] = node
+        try:
+            cur = os.sched_getaffinity(0)
+            want = cpus & cur
+            if want and want != cur:
+                self.saved = cur
+                os.sched_setaffinity(0, want)
+                self.info["bound"] = True
+                self.info["cpus"] = len(want)
+        except (AttributeError, OSError):
+            pass
+        return self
+
+    def __exit__(self, *exc):
+        import os
+
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False

@@ -1257,6 +1257,30 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     const long long T = std::max<long long>(0, it0 + Ttot - rec_lo);
     const size_t vb = (size_t)C * n * sizeof(double);
     Staged s_q0, s_var0, s_mean0, s_eps0, s_rng, s_z, s_draws;
+    // Device staging of host arrays comes from ONE arena kept in the model handle: a steady-state call makes no cudaMalloc /
+    // cudaFree at all (measured on the bench boxes, call 8 of round 2: the per-call allocations of five small input arrays
+    // cost 0.2-90 ms, and a public-API call took 20-770 ms longer than its kernel).  Everything except the draws (direct
+    // host writes, or their own buffer) and a host momentum buffer (parity tests) is lent from it.
+    const size_t ct_all = (size_t)C * (size_t)std::max<long long>(0, it0 + Ttot - rec_lo);
+    char* lend_p = nullptr;
+    size_t lend_left = 0;
+    auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    if (mem == B200_MEM_HOST) {
+        size_t need = 3 * up256(vb) + up256((size_t)C * sizeof(double)) + up256((size_t)C * sizeof(b200_pcg64));
+        if (stats) need += 12 * up256(ct_all * sizeof(double));
+        const size_t state_bytes = 6 * up256(vb) + 9 * up256((size_t)C * sizeof(double));
+        if (cfg->resume) need += state_bytes;
+        if (cfg->save) need += state_bytes;
+        CU(m->ensure_stage(need));
+        lend_p = static_cast<char*>(m->stage_arena);
+        lend_left = m->stage_bytes;
+    }
+    auto lend = [&](Staged& s, const void* user, size_t bytes) {
+        const size_t b = up256(bytes);
+        if (user && lend_p && b <= lend_left) { s.lent = lend_p; lend_p += b; lend_left -= b; }
+    };
+    lend(s_q0, q0, vb); lend(s_var0, var0, vb); lend(s_mean0, mean0, vb);
+    lend(s_eps0, eps0, (size_t)C * sizeof(double)); lend(s_rng, rng, (size_t)C * sizeof(b200_pcg64));
     if (stage_in(s_q0, q0, vb, mem, true, false, st) || stage_in(s_var0, var0, vb, mem, true, false, st) ||
         stage_in(s_mean0, mean0, vb, mem, true, false, st) ||
         stage_in(s_eps0, eps0, (size_t)C * sizeof(double), mem, true, false, st) ||
@@ -1275,13 +1299,9 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         // draws themselves.  They are staged in HBM (one arena in the model handle) and leave with 12 DMA copies at the end
         // (143 MB for the Radon bench).  The draws -- 256-byte coalesced row segments -- keep the direct path.
         const bool direct_stats = getenv("B200_DIRECT_STATS") != nullptr;
-        if (mem == B200_MEM_HOST && !direct_stats) {
-            const size_t per = (ct * sizeof(double) + 255) & ~(size_t)255;
-            CU(m->ensure_stage(12 * per));
-            for (int i = 0; i < 12; ++i) st_arr[i].lent = static_cast<char*>(m->stage_arena) + i * per;
-        }
 #define B200_ST(i, field, type)                                                              \
     if (stats->field) {                                                                      \
+        if (!direct_stats) lend(st_arr[i], stats->field, ct * sizeof(type));                 \
         if (stage_in(st_arr[i], stats->field, ct * sizeof(type), mem, false, true, st, /*direct=*/direct_stats)) return -1; \
         ds.field = (type*)st_arr[i].ptr();                                                   \
     }
@@ -1321,6 +1341,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
             if (!src) return 0;
 #define B200_SF(field, bytes, type)                                                                       \
     if (!src->field) return fail("b200_nuts_run: chain state field `" #field "` is null");               \
+    lend(st_state[slot], src->field, bytes);                                                             \
     if (stage_in(st_state[slot], src->field, bytes, mem, in, !in, st)) return -1;                        \
     dst->field = (type*)st_state[slot++].ptr();
             B200_SF(q, vb, double) B200_SF(log_step, sb, double) B200_SF(log_bar, sb, double) B200_SF(hbar, sb, double)

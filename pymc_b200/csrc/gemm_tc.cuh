@@ -2,14 +2,14 @@
 // PERFORMANCE mode of the dense Gaussian config (BASELINE #5: grad = -P q, w = Sigma g, p0 = L^-T z, v0 = L z at
 // n = 10^4).  Same arithmetic as csrc/logistic_tc.cuh: every fp64 operand is hi + lo in fp16 (22 significant bits), a
 // product is hi*hi + hi*lo + lo*hi in three kind::f16 MMAs with fp32 accumulation, and the fp32 accumulator in TMEM
-// only ever covers kGtDrain k-blocks (64 terms each) before it is drained into fp64 registers.  The fp64 DMMA kernel of
-// dense.cuh stays the parity mode.
+// only ever covers kGtDrain k-blocks (64 terms each) before it is drained into compensated fp32 register sums (kahan_add).
+// The fp64 DMMA kernel of dense.cuh stays the parity mode.
 //
 // B (the model's n x n matrices) is split once at b200_model_set_precision; A (the chains' vectors) is split by
 // gemm_tc_split_kernel before every GEMM.  Both are K-major fp16 [rows][Kpad] in HBM, TMA-loaded in 64-wide k-blocks with
 // SWIZZLE_128B.  CTA tile = 128 chains x 144 outputs: 70 x 2 = 140 tiles for n = 10^4 and 256 chains -- one wave of 148 SMs.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two warps per TMEM subpartition, 72 columns
-// each, 72 fp64 accumulators per thread).  The accumulator is double-buffered in TMEM so a drain overlaps the next MMAs.
+// each, 72 compensated fp32 sums per thread).  The accumulator is double-buffered in TMEM so a drain overlaps the next MMAs.
 #pragma once
 #include "logistic_tc.cuh"
 
@@ -33,6 +33,33 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr)
                  : "memory");
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// Compensated (Kahan) fp32 accumulation of one drained value: s + (-c) carries the running sum to ~2^-24 of its magnitude
+// independently of the number of terms, with four FADDs (128 lanes/clk/SM).  The first version of this epilogue converted
+// every drained value to fp64 (F2F.F64.F32 + DADD): ncu (profiles/r2_tc_gemm_tc_*) showed the tensor pipe 27 % busy and the
+// kernel waiting on exactly those two opcodes (22 % of the instructions each, 47 % of the stall samples) with a quarter of the
+// accumulators spilled -- the conversion unit, not the MMAs or L2 (40 % of the LTS cap), set the pace.
+#ifndef B200_GT_KAHAN
+#define B200_GT_KAHAN 1  // 0: plain round-to-nearest fp32 sums (72 registers instead of 144, one FADD per value)
+#endif
+__device__ __forceinline__ void kahan_add(float& s, float& c, float x) {
+#if B200_GT_KAHAN
+    const float y = x - c;
+    const float t = s + y;
+    c = (t - s) - y;
+    s = t;
+#else
+    s += x;
+#endif
 }
 
 struct GemmTcArgs {
@@ -137,35 +164,39 @@ __global__ void __launch_bounds__(kGtThreads, 1)
         long long chunk = 0;
         for (int tile = blockIdx.x; tile < G.n_tiles; tile += gridDim.x) {
             const int c = (tile / G.n_tiles_n) * kGtM + row, j0 = (tile % G.n_tiles_n) * kGtN;
-            double acc[kGtN / 2];
+            float sum[kGtN / 2], comp[kGtN / 2];
 #pragma unroll
-            for (int k = 0; k < kGtN / 2; ++k) acc[k] = 0.0;
+            for (int k = 0; k < kGtN / 2; ++k) { sum[k] = 0.0f; comp[k] = 0.0f; }
             for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
                 const int b = (int)(chunk & 1);
                 tc_mbar_wait(&acc_full[b], (uint32_t)((chunk >> 1) & 1));
                 tc_fence_after();
-                uint32_t v0[32], v1[32], v2[8];
-                tc_ld32(tAcc[b] + lane_addr + colA, v0);
-                tc_ld32(tAcc[b] + lane_addr + colA + 32, v1);
-                tc_ld8(tAcc[b] + lane_addr + colB, v2);
-                tc_wait_ld();
+#pragma unroll
+                for (int piece = 0; piece < 4; ++piece) {  // 16 TMEM columns at a time: 144 accumulator + 16 staging registers
+                    uint32_t v[16];
+                    tc_ld16(tAcc[b] + lane_addr + colA + 16 * piece, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) kahan_add(sum[16 * piece + k], comp[16 * piece + k], __uint_as_float(v[k]));
+                }
+                {
+                    uint32_t v[8];
+                    tc_ld8(tAcc[b] + lane_addr + colB, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) kahan_add(sum[64 + k], comp[64 + k], __uint_as_float(v[k]));
+                }
                 tc_fence_before();
                 tc_mbar_arrive(&acc_empty[b]);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) acc[k] += (double)__uint_as_float(v0[k]);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) acc[32 + k] += (double)__uint_as_float(v1[k]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[64 + k] += (double)__uint_as_float(v2[k]);
             }
             if (c < G.C) {
                 double* d = G.D + (long long)c * G.ldd + j0;
 #pragma unroll
                 for (int k = 0; k < 64; ++k)
-                    if (j0 + colA + k < G.Nout) d[colA + k] = G.alpha * acc[k];
+                    if (j0 + colA + k < G.Nout) d[colA + k] = G.alpha * ((double)sum[k] - (double)comp[k]);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (j0 + colB + k < G.Nout) d[colB + k] = G.alpha * acc[64 + k];
+                    if (j0 + colB + k < G.Nout) d[colB + k] = G.alpha * ((double)sum[64 + k] - (double)comp[64 + k]);
             }
         }
     }

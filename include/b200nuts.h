@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define B200NUTS_VERSION 200 /* 0.2.0: b200_model_desc.ir (ModelSpec IR), appended at the end of the struct */
+#define B200NUTS_VERSION 300 /* 0.3.0: B200_MASS_DENSE_ADAPT (b200_nuts_cfg.mass_update_window / .adaptation_window_multiplier,
+                              * b200_chain_summary.final_cov); 0.2.0: b200_model_desc.ir (ModelSpec IR) */
 
 /* memory space of caller-provided buffers */
 #define B200_MEM_HOST 0
@@ -133,6 +134,12 @@ typedef struct b200_ir {
 #define B200_MASS_DIAG_ADAPT_GRAD 3 /* QuadPotentialDiagAdaptExp :493-579 with use_grads (init="jitter+adapt_diag_grad",
                                      * pymc/sampling/mcmc.py:1895-1912): var = sqrt(ewvar(draws) / ewvar(gradients));
                                      * persistent engine only */
+#define B200_MASS_DENSE_ADAPT 4 /* QuadPotentialFullAdapt :748-845 + _WeightedCovariance :855-907 (init="adapt_full" /
+                                 * "jitter+adapt_full", pymc/sampling/mcmc.py:1986-2005): a dense covariance PER CHAIN, estimated
+                                 * from the tuning draws in foreground / background windows that grow by
+                                 * adaptation_window_multiplier, refreshed (with its Cholesky factor) every mass_update_window
+                                 * tuning draws.  Initial covariance = diag(var0) (init_nuts passes the identity), initial mean
+                                 * = mean0, initial weight = mass_initial_weight.  Lock-step engine; n <= 1024 */
 
 /* step methods sharing BaseHMC.astep (hmc/base_hmc.py:196-288) */
 #define B200_SAMPLER_NUTS 0 /* NUTS._hamiltonian_step          hmc/nuts.py:204-225 */
@@ -231,7 +238,8 @@ typedef struct b200_nuts_cfg {
     int32_t constrain_draws;     /* 1: draws_out holds the CONSTRAINED values (backward transforms of b200_model_set_transforms
                                   * applied where a draw is recorded: the per-draw post-processing of backends/ndarray.py:108
                                   * fused into the kernel); 0: unconstrained positions */
-    int32_t reserved;
+    int32_t mass_update_window;  /* DENSE_ADAPT: covariance + Cholesky refresh every this many tuning draws; 0 = default 1     */
+    double adaptation_window_multiplier; /* DENSE_ADAPT: window growth factor at every switch; 0 = default 2 (quadpotential.py:758) */
 } b200_nuts_cfg;
 
 /* Per-draw sampler statistics, struct-of-arrays [C][T] with T = store_warmup ? tune+draws : draws.
@@ -258,6 +266,7 @@ typedef struct b200_chain_summary {
     int32_t* bad_energy_at;  /* -1, or the iteration at which "Bad initial energy" froze the chain    */
     double* final_step_size; /* exp(log_bar) after tuning                                            */
     double* final_var;       /* [C][n] diagonal inverse-mass ("_var") at the end of the run           */
+    double* final_cov;       /* [C][n][n] DENSE_ADAPT: the chain's covariance ("_cov") at the end of the run */
 } b200_chain_summary;
 
 int b200_version(void);

@@ -292,12 +292,43 @@ def dense_any_cases():
         print(f"radon_dense_{tag}_fixed", "grad evals", int(out["stat_tree_size"].sum()), "mean depth", out["stat_depth"].mean())
 
 
+def full_adapt_cases():
+    """QuadPotentialFullAdapt (quadpotential.py:748-845; init="adapt_full", mcmc.py:1986-2005): cold start from the identity with
+    weight 10, covariance and Cholesky refreshed after every tuning draw; the short window of the Eight Schools case runs two
+    foreground <- background switches (window 15 -> 30 -> 60)."""
+    import warnings
+    qp = ref_loader.quadpotential()
+    rng = np.random.default_rng(71)
+    for name, window, tune, draws in [("eight_schools", 15, 50, 10), ("radon", 101, 30, 6)]:
+        spec = models.BUILDERS[name]()
+        n = spec.n
+        C = 2
+        q0s = [spec.initial_point() + rng.uniform(-1, 1, n) for _ in range(C)]
+        seeds = [971 + c for c in range(C)]
+        Q, ST, PR, COV = [], [], [], []
+        for c in range(C):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                pot = qp.QuadPotentialFullAdapt(n, q0s[c].copy(), np.eye(n), 10, adaptation_window=window)
+            q, sts, pre, step = run_reference_generic(spec, q0s[c], seed=seeds[c], tune=tune, draws=draws, potential=pot)
+            Q.append(q); ST.append(sts); PR.append(pre); COV.append(np.array(step.potential._cov))
+        out = dict(q0=np.array(q0s), seeds=np.array(seeds), tune=tune, draws=draws, draws_q=np.array(Q), pre_rng=np.array(PR),
+                   z=np.array([noise(s, tune + draws, n) for s in seeds]), final_cov=np.array(COV), adaptation_window=window)
+        for k in STAT_KEYS:
+            out["stat_" + k] = np.array([[s[k] for s in sts] for sts in ST])
+        np.savez_compressed(os.path.join(OUT, name + "_full_adapt.npz"), **out)
+        print(name + "_full_adapt", "grad evals", int(out["stat_tree_size"].sum()), "mean depth", out["stat_depth"].mean())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lockstep":
         lockstep_cases()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dense_any":
         dense_any_cases()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "full_adapt":
+        full_adapt_cases()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f3":
         f3_cases()

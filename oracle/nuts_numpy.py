@@ -14,6 +14,7 @@ It restates, function by function, what the reference does for one NUTS transiti
   * ``DiagMass``             <- QuadPotentialDiag / QuadPotentialDiagAdapt + _WeightedVariance
                                 hmc/quadpotential.py:582-630, :211-355, :405-448
   * ``DenseMass``            <- QuadPotentialFull        quadpotential.py:680-725
+  * ``DenseAdaptMass``       <- QuadPotentialFullAdapt + _WeightedCovariance   quadpotential.py:748-907
   * ``DiagMassExp``          <- QuadPotentialDiagAdaptExp + _ExpWeightedVariance   quadpotential.py:458-579
   * ``Oracle.hmc_draw``      <- HamiltonianMC._hamiltonian_step + unif step jitter   hmc/hmc.py:35-36, :143-200
 
@@ -186,6 +187,71 @@ class DenseInvMass(DenseMass):
 
     def momentum(self, z):
         return np.dot(self.L, z)
+
+
+class _WelfordCov:
+    """_WeightedCovariance (quadpotential.py:855-907): running mean / raw scatter matrix, divisor n - 1."""
+
+    def __init__(self, n, mean=None, cov=None, weight=0.0):
+        self.count = float(weight)
+        self.mean = np.zeros(n) if mean is None else np.array(mean, dtype="d", copy=True)
+        self.raw = np.eye(n) if cov is None else np.array(cov, dtype="d", copy=True)
+        self.raw[:] *= self.count
+
+    def add(self, x):
+        x = np.asarray(x)
+        self.count += 1
+        before = x - self.mean
+        self.mean[:] += before / self.count
+        after = x - self.mean
+        self.raw[:] += after[:, None] * before[None, :]
+
+
+class DenseAdaptMass(DenseMass):
+    """QuadPotentialFullAdapt (quadpotential.py:748-845): foreground / background sample covariances; the covariance and its
+    Cholesky factor are refreshed every `update_window` tuning draws, the windows grow by `multiplier`."""
+
+    adapt = True
+
+    def __init__(self, n, initial_mean, initial_cov=None, initial_weight=0, adaptation_window=101, multiplier=2,
+                 update_window=1):
+        if initial_cov is None:
+            initial_cov, initial_weight = np.eye(n), 1
+        self.n = n
+        self._init = (np.array(initial_mean, dtype="d"), np.array(initial_cov, dtype="d"), initial_weight,
+                      int(adaptation_window), float(multiplier), int(update_window))
+        self.rng = None
+        self.reset()
+
+    def reset(self):
+        mean, cov, weight, window, mult, upd = self._init
+        self.prev = 0
+        self.cov = cov.copy()
+        self.chol = sl.cholesky(self.cov, lower=True)
+        self.chol_error = None
+        self.fg = _WelfordCov(self.n, mean, cov, weight)
+        self.bg = _WelfordCov(self.n)
+        self.k = 0
+        self.window, self.mult, self.upd = window, mult, upd
+
+    def update(self, q, grad, tune):
+        if not tune:
+            return
+        delta = self.k - self.prev
+        self.fg.add(q)
+        self.bg.add(q)
+        if (delta + 1) % self.upd == 0:
+            np.divide(self.fg.raw, self.fg.count - 1, out=self.cov)
+            try:
+                self.chol = sl.cholesky(self.cov, lower=True)
+            except (sl.LinAlgError, ValueError) as e:  # kept and raised by raise_ok in the reference
+                self.chol_error = e
+        if delta >= self.window:
+            self.fg = self.bg
+            self.bg = _WelfordCov(self.n)
+            self.prev = self.k
+            self.window = int(self.window * self.mult)
+        self.k += 1
 
 
 # ------------------------------------------------------------------------------------------------

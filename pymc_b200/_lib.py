@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "libb200nuts.so"))  # override: A/B builds while tuning
 
 MEM_HOST, MEM_DEVICE = 0, 1
-MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE, MASS_DIAG_ADAPT_GRAD = 0, 1, 2, 3
+MASS_DIAG, MASS_DIAG_ADAPT, MASS_DENSE, MASS_DIAG_ADAPT_GRAD, MASS_DENSE_ADAPT = 0, 1, 2, 3, 4
 SAMPLER_NUTS, SAMPLER_HMC = 0, 1
 MOMENTUM_DEVICE_PHILOX, MOMENTUM_HOST_BUFFER = 0, 1
 PRECISION_FP64, PRECISION_TC_FP16X2 = 0, 1
@@ -180,7 +180,8 @@ class NutsCfg(C.Structure):
         ("resume", C.c_void_p),
         ("save", C.c_void_p),
         ("constrain_draws", C.c_int32),
-        ("reserved", C.c_int32),
+        ("mass_update_window", C.c_int32),
+        ("adaptation_window_multiplier", C.c_double),
     ]
 
 
@@ -209,6 +210,7 @@ SUMMARY_FIELDS = [
     ("bad_energy_at", np.int32),
     ("final_step_size", np.float64),
     ("final_var", np.float64),
+    ("final_cov", np.float64),
 ]
 
 

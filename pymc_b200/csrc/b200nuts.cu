@@ -19,6 +19,7 @@
 #include "logistic_tc.cuh"
 #include "gemm_tc.cuh"
 #include "lockstep.cuh"
+#include "dense_adapt.cuh"
 #include "models.cuh"
 #include "nuts_warp.cuh"
 
@@ -1063,7 +1064,10 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     const int ctile = std::max(1, env_int("B200_LS_COMPACT_TILE", 128));
     const bool compact = env_int("B200_LS_COMPACT", 1) != 0 && C > ctile;
     const int n_mats = (dense ? 8 : 2) + (compact ? 1 : 0);
-    CU(m->ensure_ls_arena(b_state + b_vecs + n_mats * b_mat + b_l + b_cnt + 3 * b_mom));
+    // DENSE_ADAPT: four n x n matrices per chain (covariance, Cholesky factor, two raw scatter matrices; dense_adapt.cuh)
+    const bool fa = P.mass_kind == B200_MASS_DENSE_ADAPT;
+    const size_t b_fa = fa ? up((size_t)C * n * n * sizeof(double)) : 0;
+    CU(m->ensure_ls_arena(b_state + b_vecs + n_mats * b_mat + b_l + b_cnt + 3 * b_mom + 4 * b_fa));
     char* a = static_cast<char*>(m->ls_arena);
     auto take = [&](size_t b) { char* p = a; a += b; return p; };
     P.state = reinterpret_cast<LsState*>(take(b_state));
@@ -1086,6 +1090,11 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     P.slot = reinterpret_cast<int*>(take(b_mom));
     int* new_slot = reinterpret_cast<int*>(take(b_mom));
     if (!compact) P.slot = nullptr;
+    if (fa) {
+        P.fa_cov = reinterpret_cast<double*>(take(b_fa));
+        P.fa_chol = reinterpret_cast<double*>(take(b_fa));
+        P.fa_raw = reinterpret_cast<double*>(take(2 * b_fa));
+    }
     // the padding columns of the request / result matrices must be zero (they are inside the GEMMs' k range) and the chain
     // vectors start from zero: clearing is bandwidth-trivial (2.6 GB at HBM speed = 0.4 ms), unlike allocating
     CU(cudaMemsetAsync(P.vecs, 0, b_vecs + n_mats * b_mat, st));
@@ -1098,11 +1107,26 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     ls_init_kernel<<<blocks, 128, 0, st>>>(P);
     CU(cudaGetLastError());
     ++launches;
+    if (fa) {
+        fa_init_kernel<<<C, kFaThreads, 0, st>>>(P);
+        CU(cudaGetLastError());
+        ++launches;
+    }
     int n_mom = dense ? C : 0;  // every chain needs the momentum of draw 0
     int C_eval = C;             // rows of the request matrices in use (shrinks when finished chains free a tile)
     for (;;) {
         if (batch_eval(m, C_eval, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
-        if (dense) {
+        if (fa) {
+            // per-chain covariance: w = Sigma_c g is a matrix-vector product per chain; a chain that finished a draw gets its
+            // potential updated (covariance, Cholesky) and the momentum of its next draw (dense_adapt.cuh)
+            fa_symv_kernel<<<C, kFaThreads, fa_smem_bytes(n), st>>>(P);
+            ++launches;
+            if (n_mom > 0) {
+                fa_update_momentum_kernel<<<n_mom, kFaThreads, fa_smem_bytes(n), st>>>(P, n_mom);
+                ++launches;
+            }
+            CU(cudaGetLastError());
+        } else if (dense) {
             // w = Sigma g for every requested point (QuadPotentialFull.velocity, quadpotential.py:705-707)
             if (gemm_nt(m, st, P.Greq, ld, C_eval, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
             ++launches;
@@ -1216,8 +1240,14 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         return fail("b200_nuts_run: treedepth must satisfy 1 <= early <= max <= %d", kMaxLevels);
     // GEMM-shaped models always advance in lock step; so does any model under a dense mass matrix (v = Sigma p is a GEMM
     // over all chains on the fp64 tensor path instead of n^2 per chain per leapfrog inside a warp)
-    const bool lockstep = is_lockstep_kind(m->kind) || cfg->mass_kind == B200_MASS_DENSE;
-    if (cfg->mass_kind == B200_MASS_DENSE) {
+    const bool lockstep = is_lockstep_kind(m->kind) || cfg->mass_kind == B200_MASS_DENSE || cfg->mass_kind == B200_MASS_DENSE_ADAPT;
+    if (cfg->mass_kind == B200_MASS_DENSE_ADAPT) {
+        if (is_lockstep_kind(m->kind)) return fail("b200_nuts_run: DENSE_ADAPT is not wired for the GEMM-shaped models (use a diagonal mass)");
+        if (n > kFaMaxN) return fail("b200_nuts_run: DENSE_ADAPT keeps four n x n matrices per chain and supports n <= %d (n = %d)", kFaMaxN, n);
+        if (cfg->mass_update_window < 0) return fail("b200_nuts_run: mass_update_window must be >= 0");
+        if (cfg->adaptation_window_multiplier < 0) return fail("b200_nuts_run: adaptation_window_multiplier must be >= 0");
+        if (!m->ld) m->ld = (long long)((n + 3) & ~3);
+    } else if (cfg->mass_kind == B200_MASS_DENSE) {
         if (!m->cov) return fail("b200_nuts_run: mass_kind DENSE needs b200_model_set_dense_mass first");
         if (m->kind == B200_MODEL_LOGISTIC) return fail("b200_nuts_run: dense mass for the logistic GLM is not wired (use a diagonal mass)");
     } else if (cfg->mass_kind == B200_MASS_DIAG_ADAPT_GRAD) {
@@ -1291,7 +1321,7 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
     // stats / summary arrays
     b200_stats ds{};
     b200_chain_summary dsum{};
-    Staged st_arr[12], sm_arr[4];
+    Staged st_arr[12], sm_arr[5];
     const size_t ct = (size_t)C * T;
     if (stats) {
         // Sampler statistics are ONE 1-8 byte value per (chain, draw) and array: written straight into host memory they are
@@ -1327,6 +1357,10 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         if (summary->final_var) {
             if (stage_in(sm_arr[3], summary->final_var, vb, mem, false, true, st, true)) return -1;
             dsum.final_var = (double*)sm_arr[3].ptr();
+        }
+        if (summary->final_cov && cfg->mass_kind == B200_MASS_DENSE_ADAPT) {
+            if (stage_in(sm_arr[4], summary->final_cov, vb * n, mem, false, true, st, true)) return -1;
+            dsum.final_cov = (double*)sm_arr[4].ptr();
         }
     }
     // draws of a frozen chain ("bad initial energy") from the failing iteration on are set to NaN by the kernels
@@ -1383,7 +1417,9 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         Q.C = C; Q.n = n; Q.tune = P.tune; Q.draws = P.draws; Q.max_td = P.max_td; Q.early_td = P.early_td;
         Q.adapt_step = P.adapt_step; Q.mass_kind = P.mass_kind; Q.momentum_source = P.momentum_source;
         Q.store_warmup = P.store_warmup; Q.window = P.window; Q.discard = P.discard; Q.chain_offset = P.chain_offset;
-        Q.dense = (cfg->mass_kind == B200_MASS_DENSE) ? 1 : 0;
+        Q.dense = (cfg->mass_kind == B200_MASS_DENSE || cfg->mass_kind == B200_MASS_DENSE_ADAPT) ? 1 : 0;
+        Q.upd_window = cfg->mass_update_window > 0 ? cfg->mass_update_window : 1;
+        Q.win_mult = cfg->adaptation_window_multiplier > 0 ? cfg->adaptation_window_multiplier : 2.0;
         Q.eps0 = P.eps0; Q.target = P.target; Q.gamma = P.gamma; Q.kappa = P.kappa; Q.t0 = P.t0; Q.Emax = P.Emax;
         Q.init_weight = P.init_weight; Q.philox_seed = P.philox_seed;
         Q.q0 = P.q0; Q.var0 = P.var0; Q.mean0 = P.mean0; Q.eps0c = P.eps0c; Q.z = P.z; Q.rng = P.rng;

@@ -52,9 +52,11 @@ __device__ __forceinline__ void ls_tiled(int lane, int n, Load&& load, Store&& s
 }
 
 struct LsState {  // per-chain scalars, resident in HBM between calls
-    int phase;    // 0 = INIT (waiting for the evaluation at q0), 1 = LEAF (waiting for a leapfrog's evaluation), 2 = DONE
+    int phase;    // 0 = INIT (waiting for the evaluation at q0), 1 = LEAF (waiting for a leapfrog's evaluation), 2 = DONE,
+                  // 3 = MASS (DENSE_ADAPT: a draw is over; waiting for the potential's update and the next momentum)
     int it, d_iter, maxd, depth, leaf, n_leaf, dir, w_idx, L_idx, R_idx, n_prop, m_pidx, c_pidx;
     int da_count, k_samples, window, fg_m, fg_v, bg_m, bg_v, bad_at, diverged, need_mom, mom_it;
+    int prev_update, fa_fg, upd_pending, chol_bad;  // DENSE_ADAPT (dense_adapt.cuh): window start, foreground slot, flags
     double eps, E0, accept_sum, max_de, m_logw, m_pe, m_plogp, c_logw, c_pe, c_plogp, cur_logp;
     double log_step, log_bar, hbar, da_mu, fg_n, bg_n;
     unsigned long long rs_hi, rs_lo, ri_hi, ri_lo;
@@ -95,6 +97,9 @@ struct LsDev {
     int* counters;                             // [0] active chains, [1] momentum requests
     int* mom_list;                             // [C] chains that requested momentum
     int logp_from_dot;                         // 1: logp = logp_const + 0.5 q.g  (Gaussian model)
+    // DENSE_ADAPT (QuadPotentialFullAdapt): per-chain matrices [C][n][n] (dense_adapt.cuh)
+    double* fa_cov; double* fa_chol; double* fa_raw;  // covariance, its lower Cholesky factor, 2 raw scatter matrices per chain
+    int upd_window; double win_mult;
 };
 
 // W = warps per chain.  W = 1: four chains per 128-thread CTA (small n); W = 8: chain = CTA, so that the O(n) vector
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     Pcg64 rng;
     rng.load(S.rs_hi, S.rs_lo, S.ri_hi, S.ri_lo);
     const bool dense = P.dense != 0;
+    const bool fa = P.mass_kind == B200_MASS_DENSE_ADAPT;  // per-chain adaptive dense mass (dense_adapt.cuh)
 
     // logp of the requested point (Gaussian: from the gradient; otherwise produced by the model kernel)
     auto req_logp = [&]() -> double {
@@ -137,7 +143,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
 
     bool begin_draw = false, next_doubling = false, start_leapfrog = false, finish_draw = false, exhausted = false;
 
-    if (S.phase == 0) {
+    if (S.phase == 3) {
+        // ---- DENSE_ADAPT: the potential has been updated and the draw's momentum is in P0n / V0n ------------------
+        begin_draw = true;
+    } else if (S.phase == 0) {
         // ---- evaluation at q0 has arrived: the start state of the first draw --------------------------------
         S.cur_logp = req_logp();
         B200_LS_UNROLL
@@ -424,7 +433,11 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         }
         ++S.it;
         if (S.it >= Ttot) S.phase = 2;
-        else begin_draw = true;
+        else if (fa) {
+            // potential.update(sample, grad, tune) (base_hmc.py:238) then potential.random() of the next draw: both need the
+            // chain's n x n matrices, so they run in fa_update_momentum_kernel between two advance calls
+            S.phase = 3; S.need_mom = 1; S.mom_it = S.it; S.upd_pending = tuning ? 1 : 0;
+        } else begin_draw = true;
     }
 
     if (begin_draw && S.phase != 2) {
@@ -453,7 +466,8 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             }
         }
         S.E0 = 0.5 * team_sum<W>(kin, lane, red) - S.cur_logp;
-        if (!isfinite(S.E0)) {  // "Bad initial energy" (base_hmc.py:205-224): freeze; the iterations that never ran are NaN
+        // a failed Cholesky (quadpotential.py:812-816, raise_ok :845-847 raises before the next draw) freezes the chain too
+        if (!isfinite(S.E0) || S.chol_bad) {  // "Bad initial energy" (base_hmc.py:205-224): freeze; the iterations that never ran are NaN
             S.bad_at = S.it;
             S.phase = 2;
             for (int t = S.it; t < Ttot; ++t) {
@@ -485,7 +499,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
             S.L_idx = S.R_idx = 0;
             S.m_logw = 0.0; S.m_pe = S.E0; S.m_plogp = S.cur_logp; S.m_pidx = 0;
             S.accept_sum = 0.0; S.max_de = 0.0; S.n_prop = 0; S.depth = 0; S.diverged = 0; S.d_iter = 0;
-            if (dense && S.it + 1 < Ttot) { S.need_mom = 1; S.mom_it = S.it + 1; }  // prefetch the next draw's momentum
+            if (dense && !fa && S.it + 1 < Ttot) { S.need_mom = 1; S.mom_it = S.it + 1; }  // prefetch the next draw's momentum
             next_doubling = true;
         }
     }
@@ -553,6 +567,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     if (S.phase == 2 && P.sm.final_var)
         B200_LS_UNROLL
         for (int i = lane; i < n; i += TS) P.sm.final_var[(long long)chain * n + i] = V(LV_VAR)[i];
+    if (S.phase == 2 && fa && P.sm.final_cov) {
+        const long long nn = (long long)n * n;
+        for (long long i = lane; i < nn; i += TS) P.sm.final_cov[chain * nn + i] = P.fa_cov[chain * nn + i];
+    }
 }
 
 // one-time initialisation of the per-chain state; requests the evaluation at q0 (and the first momentum)
@@ -579,6 +597,7 @@ __global__ void __launch_bounds__(128) ls_init_kernel(const LsDev P) {
         const double e0 = P.eps0c ? P.eps0c[chain] : P.eps0;
         S.log_step = log(e0); S.log_bar = S.log_step; S.hbar = 0.0; S.da_mu = log(10.0 * e0); S.da_count = 1;
         S.window = P.window; S.fg_m = LV_FGM; S.fg_v = LV_FGV; S.bg_m = LV_BGM; S.bg_v = LV_BGV;
+        S.prev_update = 0; S.fa_fg = 0; S.upd_pending = 0; S.chol_bad = 0;
         S.fg_n = P.init_weight; S.bg_n = 0.0;
         const b200_pcg64 r = P.rng[chain];
         S.rs_hi = r.state_hi; S.rs_lo = r.state_lo; S.ri_hi = r.inc_hi; S.ri_lo = r.inc_lo;

@@ -218,11 +218,14 @@ class CompiledModel:
                  mass_initial_weight=10.0, adaptation_window=101, discard_window=50, philox_seed=0,
                  device_outputs=False, stats=True, chain_offset=0, pinned_outputs=False, reuse_outputs=False,
                  sampler="nuts", path_length=2.0, max_steps=1024, mass_alpha=0.02, stop_adaptation=None, constrain=False,
-                 iter_begin=0, iter_count=None, resume=None, save=None):
+                 iter_begin=0, iter_count=None, resume=None, save=None, window_multiplier=None, update_window=1):
         """Run C chains for tune+draws NUTS iterations inside one persistent kernel.
 
         ``sampler="hmc"`` runs HamiltonianMC (hmc/hmc.py: ``path_length``, ``max_steps``; pass ``target_accept=0.65`` for
-        its default); ``mass="diag_adapt_grad"`` is init="jitter+adapt_diag_grad" (``mass_alpha``, ``stop_adaptation``).
+        its default); ``mass="diag_adapt_grad"`` is init="jitter+adapt_diag_grad" (``mass_alpha``, ``stop_adaptation``);
+        ``mass="dense_adapt"`` is QuadPotentialFullAdapt (init="adapt_full"): a dense covariance per chain estimated from
+        the tuning draws (``adaptation_window``, ``window_multiplier`` default 2, ``update_window``); initial covariance
+        diag(``var0``), initial mean ``mean0``, weight ``mass_initial_weight``; ``summary["final_cov"]`` holds the result.
         ``iter_begin`` / ``iter_count`` run a slice of the ``tune + draws`` schedule; ``resume`` / ``save`` are ``ChainState``
         objects (host arrays) carrying the chains between calls: a run split into slices is bit-identical to the
         uninterrupted run (persistent engine; outputs and ``z`` then cover the slice only).
@@ -247,7 +250,9 @@ class CompiledModel:
         cfg.max_treedepth, cfg.early_max_treedepth = int(max_treedepth), int(early_max_treedepth)
         cfg.adapt_step_size = int(bool(adapt_step_size))
         cfg.mass_kind = {"diag": _lib.MASS_DIAG, "diag_adapt": _lib.MASS_DIAG_ADAPT, "dense": _lib.MASS_DENSE,
-                         "diag_adapt_grad": _lib.MASS_DIAG_ADAPT_GRAD}[mass]
+                         "diag_adapt_grad": _lib.MASS_DIAG_ADAPT_GRAD, "dense_adapt": _lib.MASS_DENSE_ADAPT}[mass]
+        cfg.mass_update_window = int(update_window)
+        cfg.adaptation_window_multiplier = 0.0 if window_multiplier is None else float(window_multiplier)
         cfg.sampler = {"nuts": _lib.SAMPLER_NUTS, "hmc": _lib.SAMPLER_HMC}[sampler]
         cfg.path_length, cfg.max_steps = float(path_length), int(max_steps)
         cfg.mass_alpha = float(mass_alpha)
@@ -344,7 +349,12 @@ class CompiledModel:
                 setattr(st, name, _lib.ptr(st_arr[name]))
         sm, sm_arr = _lib.ChainSummary(), {}
         for name, dt in _lib.SUMMARY_FIELDS:
-            sm_arr[name] = mk((Cn, self.n) if name == "final_var" else (Cn,), dt)
+            if name == "final_cov":
+                if mass != "dense_adapt":
+                    continue
+                sm_arr[name] = mk((Cn, self.n, self.n), dt)
+            else:
+                sm_arr[name] = mk((Cn, self.n) if name == "final_var" else (Cn,), dt)
             setattr(sm, name, _lib.ptr(sm_arr[name]))
 
         _lib.check(

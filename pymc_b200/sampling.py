@@ -137,7 +137,9 @@ def sample_b200_nuts(
     a ``CompiledModel``.  ``nuts_kwargs`` accepts the ``pm.NUTS`` / ``pm.HamiltonianMC`` keywords ``max_treedepth,
     early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size, path_length, max_steps``.
     ``init`` (pm.sample / init_nuts, pymc/sampling/mcmc.py:1759-2021): "auto" = "jitter+adapt_diag"; "adapt_diag";
-    "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250).
+    "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250);
+    "adapt_full" / "jitter+adapt_full" (QuadPotentialFullAdapt: a dense covariance per chain, identity start, weight 10,
+    mcmc.py:1986-2005).
     ``step``: "nuts" (target_accept default 0.8) or "hmc" (HamiltonianMC, default 0.65).
     ``momentum="numpy"`` draws the momentum normals from each chain's NumPy potential stream exactly like
     the reference (host-generated, uploaded); ``"device"`` generates them on the GPU (Philox).
@@ -173,8 +175,11 @@ def sample_b200_nuts(
         mass = "diag_adapt_grad"
         nk.setdefault("mass_alpha", 0.02)
         nk.setdefault("stop_adaptation", tune - 50 if tune > 250 else None)  # mcmc.py:1900-1903
+    elif init == "adapt_full":
+        mass = "dense_adapt"  # QuadPotentialFullAdapt(n, mean, eye, 10): mcmc.py:1986-2005
     else:
-        raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag and (jitter+)adapt_diag_grad")
+        raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag, (jitter+)adapt_diag_grad and "
+                         "(jitter+)adapt_full")
     mass = nk.pop("mass", mass)  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
 
     from . import parallel

@@ -25,16 +25,16 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200nuts.h but not exported"
     assert {s[0] for s in _lib.SYMBOLS} == set(names), "ctypes table and header disagree"
-    assert lib.b200_version() == 200
+    assert lib.b200_version() == 300
 
 
 def test_struct_layouts_match_header():
     # field order/size of the ctypes mirrors (a mismatch would corrupt arguments silently)
     assert ctypes.sizeof(_lib.Pcg64State) == 32 and _lib.PCG64_DTYPE.itemsize == 32
     lib = _lib.load()
-    assert ctypes.sizeof(_lib.NutsCfg) == lib.b200_struct_size(1) == 176 and ctypes.sizeof(_lib.ChainStateC) == lib.b200_struct_size(13)
+    assert ctypes.sizeof(_lib.NutsCfg) == lib.b200_struct_size(1) == 184 and ctypes.sizeof(_lib.ChainStateC) == lib.b200_struct_size(13)
     assert ctypes.sizeof(_lib.Stats) == 12 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(_lib.ChainSummary) == 4 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.ChainSummary) == 5 * ctypes.sizeof(ctypes.c_void_p) == lib.b200_struct_size(3)
     assert _lib.ModelDesc.n_obs.offset == 8 and _lib.ModelDesc.x.offset == 24
 
 

@@ -1,0 +1,135 @@
+"""QuadPotentialFullAdapt (hmc/quadpotential.py:748-845, _WeightedCovariance :855-907) -- the potential
+behind init="adapt_full" / "jitter+adapt_full" (sampling/mcmc.py:1986-2005).
+
+Goldens come from the verbatim reference (oracle/make_golden.py full_adapt): cold start from the identity with weight 10,
+covariance + Cholesky refreshed after every tuning draw; the Eight Schools case uses a 15-draw window so the run crosses two
+foreground <- background switches.  CPU: the oracle restatement reproduces them bit for bit.  GPU: the lock-step engine with a
+covariance PER CHAIN (csrc/dense_adapt.cuh) follows the reference chain -- every discrete statistic identical over the prefix
+asserted below; the estimator arithmetic is NumPy's, while Cholesky / triangular solve / matrix-vector products sum in their
+own order, so positions agree to a tolerance and the first divergent draw is reported (adaptive dynamics are chaotic)."""
+import numpy as np
+import pytest
+
+from b200_helpers import relerr, start_states
+from pymc_b200 import models
+from test_f3_variants import _gen
+
+SPEC = {"eight_schools": models.eight_schools, "radon": models.radon}
+
+
+@pytest.mark.parametrize("name", ["eight_schools", "radon"])
+def test_oracle_full_adapt_reproduces_reference_golden(golden, name):
+    from oracle import logp_numpy, nuts_numpy
+
+    d = golden(name + "_full_adapt")
+    spec = SPEC[name]()
+    f = logp_numpy.make_logp(spec)
+    for c in range(len(d["seeds"])):
+        mass = nuts_numpy.DenseAdaptMass(spec.n, d["q0"][c].copy(), np.eye(spec.n), 10, adaptation_window=int(d["adaptation_window"]))
+        o = nuts_numpy.Oracle(f, mass)
+        o.rng = _gen(d["pre_rng"][c][0])
+        qs, st = o.run(d["q0"][c], int(d["tune"]), int(d["draws"]), z=d["z"][c])
+        assert np.array_equal(st["tree_size"], d["stat_tree_size"][c])
+        assert np.array_equal(qs, d["draws_q"][c])
+        assert np.array_equal(mass.cov, d["final_cov"][c])
+
+
+def test_full_adapt_window_schedule():
+    """The estimator windows of the restatement: switch when delta >= window, window <- int(window * multiplier)."""
+    from oracle import nuts_numpy
+
+    n = 3
+    m = nuts_numpy.DenseAdaptMass(n, np.zeros(n), np.eye(n), 10, adaptation_window=4, multiplier=2)
+    rng = np.random.default_rng(0)
+    switches = []
+    for k in range(40):
+        before = m.prev
+        m.update(rng.normal(size=n), None, True)
+        if m.prev != before:
+            switches.append(k)
+    assert switches == [4, 12, 28] and m.window == 32
+    L = m.chol
+    assert np.allclose(L @ L.T, m.cov, rtol=1e-12, atol=1e-12) and np.allclose(m.cov, m.cov.T, rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["eight_schools", "radon"])
+def test_gpu_full_adapt_follows_the_reference_chain(golden, name):
+    from pymc_b200 import engine
+    from test_gpu_fullsize import _report
+
+    d = golden(name + "_full_adapt")
+    cm = engine.CompiledModel(SPEC[name]())
+    tune, draws = int(d["tune"]), int(d["draws"])
+    T = tune + draws
+    res = cm.nuts_run(d["q0"], start_states(d), tune=tune, draws=draws, z=d["z"], mass="dense_adapt", mean0=d["q0"],
+                      adaptation_window=int(d["adaptation_window"]))
+    first_bad, err_at = [], []
+    for c in range(len(d["seeds"])):
+        same = (res.stats["tree_size"][c] == d["stat_tree_size"][c]) & (res.stats["depth"][c] == d["stat_depth"][c]) & \
+               (res.stats["index_in_trajectory"][c] == d["stat_index_in_trajectory"][c])
+        fb = int(np.argmin(same)) if not same.all() else T
+        first_bad.append(fb)
+        err_at.append(float(np.max(np.abs(res.draws[c][:max(fb, 1)] - d["draws_q"][c][:max(fb, 1)]))))
+    _report("first_divergent_draw/" + name + "_full_adapt", {"first_tree_mismatch_per_chain": first_bad, "draws": T,
+                                                             "max_abs_position_error_before_it": err_at,
+                                                             "adaptation_window": int(d["adaptation_window"])})
+    # the covariance feeds back into the dynamics from the first draw on (update_window = 1)
+    assert max(first_bad) >= (30 if name == "eight_schools" else 12), first_bad
+    c = int(np.argmax(first_bad))
+    m = slice(0, min(first_bad[c], 20))
+    assert np.max(np.abs(res.draws[c][m] - d["draws_q"][c][m])) <= 1e-6
+    assert np.max(np.abs(res.draws[c][:8] - d["draws_q"][c][:8])) <= 1e-9
+    assert relerr(res.stats["step_size"][c][m], d["stat_step_size"][c][m]) <= 1e-6
+    assert relerr(res.stats["energy"][c][:8], d["stat_energy"][c][:8]) <= 1e-9
+    if first_bad[c] == T:  # on the reference path to the end: the adapted covariance is the reference's
+        cov = res.summary["final_cov"][c]
+        assert np.max(np.abs(cov - d["final_cov"][c])) <= 1e-5 * np.max(np.abs(d["final_cov"][c]))
+    assert np.all(res.summary["bad_energy_at"] == -1)
+
+
+@pytest.mark.gpu
+def test_gpu_full_adapt_posterior_and_covariance():
+    """Free-running statistical check: 64 Eight-Schools chains with init="jitter+adapt_full" reproduce the posterior of the
+    same chains under jitter+adapt_diag (means within 4 MCSE), and every chain's adapted covariance is symmetric positive
+    definite with the posterior's scale."""
+    import pymc_b200
+
+    spec = models.eight_schools()
+    kw = dict(tune=400, chains=64, random_seed=11, model=spec, compute_convergence_checks=False, keep_untransformed=True)
+    full = pymc_b200.sample_b200_nuts(300, init="jitter+adapt_full", **kw)
+    diag = pymc_b200.sample_b200_nuts(300, init="jitter+adapt_diag", **kw)
+    a, b = full.unconstrained, diag.unconstrained
+    ma, mb = a.mean(axis=(0, 1)), b.mean(axis=(0, 1))
+    # MCSE from the chain means (independent chains)
+    se = np.sqrt(a.mean(axis=1).var(axis=0, ddof=1) / a.shape[0] + b.mean(axis=1).var(axis=0, ddof=1) / b.shape[0])
+    zmax = float(np.max(np.abs(ma - mb) / se))
+    from test_gpu_fullsize import _report
+
+    _report("full_adapt/eight_schools_posterior", {"max_z_of_means_vs_adapt_diag": zmax, "chains": 64, "draws": 300,
+                                                   "divergent_fraction": float(np.mean(full.sample_stats["diverging"]))})
+    assert zmax < 4.5, zmax
+    sd_ratio = a.std(axis=(0, 1)) / b.std(axis=(0, 1))
+    assert np.all(sd_ratio > 0.8) and np.all(sd_ratio < 1.25), sd_ratio
+
+
+@pytest.mark.gpu
+def test_gpu_full_adapt_final_covariance_is_spd_and_update_window():
+    from pymc_b200 import engine
+    from pymc_b200 import rng as brng
+
+    spec = models.eight_schools()
+    cm = engine.CompiledModel(spec)
+    C, T = 8, 120
+    sr, pr, _ = brng.chain_generators(5, C)
+    q0 = spec.initial_point()[None] + np.random.default_rng(2).uniform(-1, 1, (C, spec.n))
+    for upd in (1, 7):
+        res = cm.nuts_run(q0, brng.pack_pcg64(sr), tune=T, draws=5, mass="dense_adapt", mean0=q0, update_window=upd,
+                          adaptation_window=40, philox_seed=3)
+        cov = res.summary["final_cov"]
+        assert cov.shape == (C, spec.n, spec.n) and np.all(np.isfinite(cov))
+        for c in range(C):
+            assert np.max(np.abs(cov[c] - cov[c].T)) <= 1e-9 * np.max(np.abs(cov[c]))
+            assert np.linalg.eigvalsh(0.5 * (cov[c] + cov[c].T)).min() > 0
+        assert np.all(res.summary["bad_energy_at"] == -1)

@@ -75,6 +75,38 @@ def test_dense_mass_matches_reference():
     assert np.array_equal(np.array(qs), qo)
 
 
+@pytest.mark.parametrize("name,tune,draws", [("eight_schools", 130, 10), ("radon", 60, 5)])
+def test_dense_adapt_mass_matches_reference(name, tune, draws):
+    """QuadPotentialFullAdapt (quadpotential.py:748-845, init="adapt_full": mcmc.py:1986-1996) vs DenseAdaptMass, through the
+    first window switch for Eight Schools (foreground <- background at delta = 101)."""
+    import warnings
+    spec = models.BUILDERS[name]()
+    n = spec.n
+    f = logp_numpy.make_logp(spec)
+    q0 = spec.initial_point() + np.random.default_rng(4).uniform(-1, 1, n)
+    qp = ref_loader.quadpotential()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pot = qp.QuadPotentialFullAdapt(n, q0.copy(), np.eye(n), 10)
+    start = {v.name: q0[v.offset : v.offset + v.size].copy() for v in spec.vars}
+    step, _ = ref_loader.make_nuts(f, spec.var_sizes, start, potential=pot, step_rng=0, adapt_step_size=True)
+    step.setup_chain(np.random.default_rng(91), tune, draws)
+    pt, qs, sts = start, [], []
+    for i in range(tune + draws):
+        if i == tune:
+            step.stop_tuning()
+        pt, st = step.step(pt)
+        qs.append(np.concatenate([np.ravel(pt[v.name]) for v in spec.vars]))
+        sts.append(st[0])
+    o = nuts_numpy.Oracle(f, nuts_numpy.DenseAdaptMass(n, q0.copy(), np.eye(n), 10))
+    o.setup_chain(np.random.default_rng(91))
+    qo, so = o.run(q0, tune, draws)
+    assert np.array_equal(np.array(qs), qo)
+    for k in ("tree_size", "depth", "index_in_trajectory", "energy", "step_size"):
+        assert np.array_equal(np.array([s[k] for s in sts]), so[k]), k
+    assert np.array_equal(step.potential._cov, o.mass.cov) and np.array_equal(step.potential._chol, o.mass.chol)
+
+
 def test_loader_self_check_known_answer():
     """five Eight-Schools draws of the verbatim reference (depth, tree_size, index_in_trajectory)."""
     spec = models.eight_schools()

@@ -197,6 +197,13 @@ def _pin_worker(cpus, procs, counter):
         pass
 
 
+def summary_matrix(summary):
+    """Per-chain scalar summaries (grad_evals, bad_energy_at, final_step_size, ...) as one [chains, k] float64 matrix for the
+    gather to rank 0; per-chain VECTORS (final_var [chains, n], final_cov) stay with the rank that holds the chains."""
+    cols = [np.asarray(v, dtype=np.float64) for v in summary.values() if np.ndim(v) == 1]
+    return np.stack(cols, axis=1)
+
+
 def make_pool(procs):
     import multiprocessing as mp
 
@@ -531,8 +538,7 @@ def b200_arm(args):
                 # links in parallel).  What rank 0 needs of the other ranks for the run's report -- the per-chain summaries
                 # (step size, tree statistics, evaluation counts) -- is gathered to rank 0 over NCCL here, inside the timed
                 # region.  The cost of gathering the DRAWS themselves to rank 0's HBM is measured separately below.
-                summ_all, _ = parallel.gather_chains(
-                    np.stack([np.asarray(v, dtype=np.float64) for v in res_h.summary.values()], axis=1), {}, chains_total, dst=0)
+                summ_all, _ = parallel.gather_chains(summary_matrix(res_h.summary), {}, chains_total, dst=0)
         torch.cuda.synchronize()
         dt = parallel.max_over_ranks(time.perf_counter() - t0)
         ev_all = parallel.sum_over_ranks(float(ev_tot))
@@ -553,6 +559,9 @@ def b200_arm(args):
     # ---- N > 1: what gathering every rank's draws to rank 0 costs (NCCL gather over NVLink into rank 0's HBM) ---------
     gather_info = None
     if world > 1:
+        # one small untimed gather first: NCCL builds the communicator's gather channels lazily (1-3 s on the first call,
+        # which the r2_scale_* lines of the multi-GPU call still include in their gather figure)
+        parallel.gather_chains(res.draws[:, :1], {}, chains_total, dst=0)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

@@ -1059,7 +1059,7 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
     P.vec_stride = ls_vec_count(P.max_td) * n;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_state = up((size_t)C * sizeof(LsState)), b_vecs = up((size_t)C * P.vec_stride * sizeof(double)), b_mat = up(mat);
-    const size_t b_l = up((size_t)C * sizeof(double)), b_cnt = up(2 * sizeof(int)), b_mom = up((size_t)C * sizeof(int));
+    const size_t b_l = up((size_t)C * sizeof(double)), b_cnt = up(4 * sizeof(int)), b_mom = up((size_t)C * sizeof(int));
     // compaction of the request rows once finished chains free a whole tile of them (lockstep.cuh: ls_compact_*)
     const int ctile = std::max(1, env_int("B200_LS_COMPACT_TILE", 128));
     const bool compact = env_int("B200_LS_COMPACT", 1) != 0 && C > ctile;
@@ -1113,6 +1113,15 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
         ++launches;
     }
     int n_mom = dense ? C : 0;  // every chain needs the momentum of draw 0
+    bool serve = true;
+    // Deferred momentum (fixed dense mass).  A chain asks for the momentum of draw it+1 when draw `it` begins, so the request
+    // has the length of a draw to be served.  The two momentum GEMMs stream their n x n matrices whatever the number of
+    // requesting rows (for n = 10^4 they cost as much as the gradient and mass GEMMs of ALL chains), so requests are queued on
+    // the device and served in batches: when half of the live chains are waiting in the queue, or as soon as a chain reaches
+    // the end of its draw without its momentum (it then idles for one round: LsState phase 3).  The noise z of (chain, draw)
+    // does not depend on when it is served, so results are identical for every threshold.  B200_LS_MOM_DEFER=0: serve every round.
+    const double defer = fa ? 0.0 : std::max(0.0, std::min(1.0, env_int("B200_LS_MOM_DEFER", 50) / 100.0));
+    CU(cudaMemsetAsync(P.counters, 0, 4 * sizeof(int), st));
     int C_eval = C;             // rows of the request matrices in use (shrinks when finished chains free a tile)
     for (;;) {
         if (batch_eval(m, C_eval, P.Qreq, P.Greq, P.logp_req, bs, st, &launches)) return -1;
@@ -1124,19 +1133,21 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
             if (n_mom > 0) {
                 fa_update_momentum_kernel<<<n_mom, kFaThreads, fa_smem_bytes(n), st>>>(P, n_mom);
                 ++launches;
+                CU(cudaMemsetAsync(P.counters + 2, 0, sizeof(int), st));
             }
             CU(cudaGetLastError());
         } else if (dense) {
             // w = Sigma g for every requested point (QuadPotentialFull.velocity, quadpotential.py:705-707)
             if (gemm_nt(m, st, P.Greq, ld, C_eval, m->cov, ld, n, (int)ld, 1.0, P.Wreq, ld)) return -1;
             ++launches;
-            if (n_mom > 0) {
+            if (serve && n_mom > 0) {
                 ls_gather_z_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, Zb);
                 // p0 = L^-T z (solve_triangular(chol.T, z), quadpotential.py:710-713);  v0 = Sigma p0 = L z
                 if (gemm_nt(m, st, Zb, ld, n_mom, m->linvT, ld, n, (int)ld, 1.0, P0b, ld)) return -1;
                 if (gemm_nt(m, st, Zb, ld, n_mom, m->chol, ld, n, (int)ld, 1.0, V0b, ld)) return -1;
                 ls_scatter_mom_kernel<<<n_mom, 256, 0, st>>>(P, n_mom, P0b, V0b);
                 CU(cudaGetLastError());
+                CU(cudaMemsetAsync(P.counters + 2, 0, sizeof(int), st));
                 launches += 4;
             }
         }
@@ -1148,11 +1159,12 @@ static int run_lockstep(b200_model* m, LsDev P, cudaStream_t st) {
         else ls_advance_kernel<1><<<blocks, 128, 0, st>>>(P);
         CU(cudaGetLastError());
         ++launches;
-        int h[2];
+        int h[3];
         CU(cudaMemcpyAsync(h, P.counters, sizeof h, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (h[0] == 0) break;
-        n_mom = dense ? h[1] : 0;
+        n_mom = dense ? h[2] : 0;
+        serve = h[1] > 0 || n_mom >= std::max(1, (int)(defer * h[0]));
         if (compact && (h[0] + ctile - 1) / ctile < (C_eval + ctile - 1) / ctile) {
             ls_compact_slots_kernel<<<1, 1024, 0, st>>>(P, new_slot);
             ls_compact_move_kernel<<<C, 256, 0, st>>>(P, new_slot, Qalt);

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kFaThreads) fa_update_momentum_kernel(const Ls
     if (tid == 0) {
         SP->k_samples = k_samples; SP->window = window; SP->prev_update = prev; SP->fa_fg = fa_fg;
         SP->fg_m = fg_m; SP->bg_m = bg_m; SP->fg_n = fg_n; SP->bg_n = bg_n; SP->upd_pending = 0; SP->chol_bad = chol_bad;
+        SP->mom_have = it;
     }
 }
 

@@ -53,10 +53,13 @@ __device__ __forceinline__ void ls_tiled(int lane, int n, Load&& load, Store&& s
 
 struct LsState {  // per-chain scalars, resident in HBM between calls
     int phase;    // 0 = INIT (waiting for the evaluation at q0), 1 = LEAF (waiting for a leapfrog's evaluation), 2 = DONE,
-                  // 3 = MASS (DENSE_ADAPT: a draw is over; waiting for the potential's update and the next momentum)
+                  // 3 = MASS (dense mass: a draw is over and the next draw's momentum has not been served yet -- DENSE_ADAPT
+                  //     always stops here for the potential's update; a fixed dense mass only when its prefetch is still
+                  //     queued, see "deferred momentum" in b200nuts.cu run_lockstep)
     int it, d_iter, maxd, depth, leaf, n_leaf, dir, w_idx, L_idx, R_idx, n_prop, m_pidx, c_pidx;
     int da_count, k_samples, window, fg_m, fg_v, bg_m, bg_v, bad_at, diverged, need_mom, mom_it;
     int prev_update, fa_fg, upd_pending, chol_bad;  // DENSE_ADAPT (dense_adapt.cuh): window start, foreground slot, flags
+    int mom_have;  // dense mass: the iteration whose momentum (p0, v0) currently sits in the chain's rows of P0n / V0n
     double eps, E0, accept_sum, max_de, m_logw, m_pe, m_plogp, c_logw, c_pe, c_plogp, cur_logp;
     double log_step, log_bar, hbar, da_mu, fg_n, bg_n;
     unsigned long long rs_hi, rs_lo, ri_hi, ri_lo;
@@ -94,7 +97,8 @@ struct LsDev {
     double* logp_req;                          // [C] (models that return logp from their own kernel)
     double* P0n; double* V0n;                  // prefetched momentum of the next draw [C][ld] (dense mass)
     int* slot;                                 // [C] row of chain c in the request / result matrices (compaction; null: c)
-    int* counters;                             // [0] active chains, [1] momentum requests
+    int* counters;                             // [0] active chains, [1] chains stalled on their momentum (both per advance),
+                                               // [2] momentum requests queued since the last service
     int* mom_list;                             // [C] chains that requested momentum
     int logp_from_dot;                         // 1: logp = logp_const + 0.5 q.g  (Gaussian model)
     // DENSE_ADAPT (QuadPotentialFullAdapt): per-chain matrices [C][n][n] (dense_adapt.cuh)
@@ -440,6 +444,13 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
         } else begin_draw = true;
     }
 
+    bool stalled = false;
+    if (begin_draw && S.phase != 2 && dense && S.mom_have != S.it) {
+        // the draw's momentum is still in the request queue (the host serves requests in batches): wait one round
+        S.phase = 3;
+        begin_draw = false;
+        stalled = true;
+    }
     if (begin_draw && S.phase != 2) {
         team_sync<W>();
         const bool tuning = S.it < P.tune;
@@ -552,7 +563,8 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) ls_advance_kernel(const
     S.rs_hi = (unsigned long long)(rng.state >> 64); S.rs_lo = (unsigned long long)rng.state;
     if (lane == 0) {
         if (S.phase != 2) atomicAdd(&P.counters[0], 1);
-        if (S.need_mom) { const int j = atomicAdd(&P.counters[1], 1); P.mom_list[j] = chain; }
+        if (stalled) atomicAdd(&P.counters[1], 1);
+        if (S.need_mom) { const int j = atomicAdd(&P.counters[2], 1); P.mom_list[j] = chain; }
         if (S.phase == 2) {
             b200_pcg64 r;
             r.state_hi = S.rs_hi; r.state_lo = S.rs_lo; r.inc_hi = S.ri_hi; r.inc_lo = S.ri_lo;
@@ -597,7 +609,7 @@ __global__ void __launch_bounds__(128) ls_init_kernel(const LsDev P) {
         const double e0 = P.eps0c ? P.eps0c[chain] : P.eps0;
         S.log_step = log(e0); S.log_bar = S.log_step; S.hbar = 0.0; S.da_mu = log(10.0 * e0); S.da_count = 1;
         S.window = P.window; S.fg_m = LV_FGM; S.fg_v = LV_FGV; S.bg_m = LV_BGM; S.bg_v = LV_BGV;
-        S.prev_update = 0; S.fa_fg = 0; S.upd_pending = 0; S.chol_bad = 0;
+        S.prev_update = 0; S.fa_fg = 0; S.upd_pending = 0; S.chol_bad = 0; S.mom_have = -1;
         S.fg_n = P.init_weight; S.bg_n = 0.0;
         const b200_pcg64 r = P.rng[chain];
         S.rs_hi = r.state_hi; S.rs_lo = r.state_lo; S.ri_hi = r.inc_hi; S.ri_lo = r.inc_lo;
@@ -669,6 +681,7 @@ __global__ void __launch_bounds__(256) ls_scatter_mom_kernel(const LsDev P, int 
         P.P0n[(long long)chain * P.ld + i] = P0b[(long long)j * P.ld + i];
         P.V0n[(long long)chain * P.ld + i] = V0b[(long long)j * P.ld + i];
     }
+    if (threadIdx.x == 0) P.state[chain].mom_have = P.state[chain].mom_it;
 }
 
 }  // namespace b200

@@ -115,6 +115,15 @@ WORKER = textwrap.dedent(
     N, pm_, pM2 = parallel.pool_welford(cnt[lo:hi], mu[lo:hi], m2[lo:hi])
     N1 = cnt.sum(); m1 = (cnt[:, None] * mu).sum(0) / N1; M1 = (m2 + cnt[:, None] * (mu - m1) ** 2).sum(0)
     assert abs(N - N1) < 1e-12 and np.allclose(pm_, m1, rtol=1e-13) and np.allclose(pM2, M1, rtol=1e-11)
+    # bench.py's N > 1 e2e leg: the per-chain scalar summaries of an engine result (which also carries [chains, n] vectors)
+    import bench
+    summ = {{"grad_evals": np.arange(lo, hi, dtype=np.int64), "bad_energy_at": np.full(hi - lo, -1, dtype=np.int32),
+            "final_step_size": np.linspace(0.1, 0.2, chains)[lo:hi], "final_var": np.ones((hi - lo, n))}}
+    sm, _ = parallel.gather_chains(bench.summary_matrix(summ), {{}}, chains, dst=0)
+    if dist.get_rank() == 0:
+        assert sm.shape == (chains, 3) and np.array_equal(sm[:, 0], np.arange(chains)) and np.all(sm[:, 1] == -1)
+    else:
+        assert sm is None
     assert parallel.max_over_ranks(float(dist.get_rank())) == 1.0
     assert parallel.sum_over_ranks(1.5) == 3.0
     dist.destroy_process_group()

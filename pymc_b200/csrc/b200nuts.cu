@@ -98,6 +98,7 @@ struct b200_model {
     int precision = B200_PRECISION_FP64;
     const __half* Xh = nullptr;
     const __half* Xl = nullptr;
+    const float* y32 = nullptr;
     long long tc_slabs = 0;
     CUtensorMap map_hi{}, map_lo{};
     // dense Gaussian, tensor-core performance mode (csrc/gemm_tc.cuh): fp16 pieces of the n x n matrices (B operands) and the
@@ -941,6 +942,13 @@ static int prepare_logistic_tc(b200_model* m) {
     CU(cudaDeviceSynchronize());
     m->Xh = (const __half*)h;
     m->Xl = (const __half*)l;
+    void* y32 = nullptr;  // labels as fp32, padded to whole slabs: travel with the slab (logistic_tc2_kernel)
+    CU(cudaMalloc(&y32, (size_t)rows_pad * sizeof(float)));
+    m->owned.push_back(y32);
+    logistic_tc_y_kernel<<<(unsigned)((rows_pad + 255) / 256), 256>>>(m->y8, m->n_rows, (float*)y32, rows_pad);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    m->y32 = (const float*)y32;
     if (make_x_map(&m->map_hi, m->Xh, rows_pad) || make_x_map(&m->map_lo, m->Xl, rows_pad)) return -1;
     return 0;
 }
@@ -1006,10 +1014,17 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
         if (m->KP != kTcK) {  // partials are [.][.][KP]: the tensor-core kernel writes 128-wide rows
             return fail("tensor-core mode needs the 128-feature layout (65..128 features); this model has %d", m->n);
         }
-        auto kern = logistic_tc_kernel;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        LogisticTcArgs A{m->y8, m->n_rows, m->tc_slabs, Q, ld, C, m->n, bs.gpart.as<double>(), bs.lpart.as<double>(), bs.cpad};
-        kern<<<dim3(bs.gx, bs.cpad / kLogiChains), kTcThreads, kTcSmemBytes, st>>>(m->map_hi, m->map_lo, A);
+        if (env_int("B200_LOGI_TC_V", 2) == 1) {  // version 1 of the kernel (8 epilogue warps, drains through global memory)
+            auto kern = logistic_tc_kernel;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+            LogisticTcArgs A{m->y8, m->n_rows, m->tc_slabs, Q, ld, C, m->n, bs.gpart.as<double>(), bs.lpart.as<double>(), bs.cpad};
+            kern<<<dim3(bs.gx, bs.cpad / kLogiChains), kTcThreads, kTcSmemBytes, st>>>(m->map_hi, m->map_lo, A);
+        } else {
+            auto kern = logistic_tc2_kernel;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc2SmemBytes));
+            LogisticTc2Args A{m->y32, m->n_rows, m->tc_slabs, Q, ld, C, m->n, bs.gpart.as<double>(), bs.lpart.as<double>(), bs.cpad};
+            kern<<<dim3(bs.gx, bs.cpad / kLogiChains), kTc2Threads, kTc2SmemBytes, st>>>(m->map_hi, m->map_lo, A);
+        }
         CU(cudaGetLastError());
     } else
     switch (m->KP) {

@@ -454,7 +454,9 @@ struct LogisticTc2Args {
     int Cpad;
 };
 
-__global__ void __maxnreg__(112)
+// 18 warps on 4 schedulers: one scheduler hosts 5 of them, and the register file is per scheduler (16 K entries), so the
+// kernel gets 96 registers per thread, not 65536 / 576 = 113 (a 112-register build fails to launch: measured, call 11)
+__global__ void __launch_bounds__(kTc2Threads, 1)
     logistic_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const LogisticTc2Args A) {
     extern __shared__ char tc_smem_raw[];
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);

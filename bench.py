@@ -413,11 +413,19 @@ def b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # B200_BENCH_ONE_GPU=1: every rank uses GPU 0 and the ranks talk over gloo -- NOT a measurement, a way to run the N > 1 host
+    # logic of this file (sharding, the gathers, max-over-ranks timing) on a one-GPU box; the line says so ("debug")
+    one_gpu = world > 1 and os.environ.get("B200_BENCH_ONE_GPU") == "1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
     wl = args.wl
@@ -561,7 +569,7 @@ def b200_arm(args):
     if world > 1:
         # one small untimed gather first: NCCL builds the communicator's gather channels lazily (1-3 s on the first call,
         # which the r2_scale_* lines of the multi-GPU call still include in their gather figure)
-        parallel.gather_chains(res.draws[:, :1], {}, chains_total, dst=0)
+        parallel.gather_chains(res.draws[:, :1].contiguous(), {}, chains_total, dst=0)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -632,6 +640,8 @@ def b200_arm(args):
             "ess": {"min_bulk_ess_last_step": ess_min, "ess_per_sec": ess_min / step_s, "chains": C, "draws": draws},
             "grad_evals_incl_start_state": all_evals * world, "divergent_fraction": div_frac,
         }
+        if one_gpu:
+            line["debug"] = "B200_BENCH_ONE_GPU=1: all ranks shared GPU 0 over gloo; not a measurement"
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

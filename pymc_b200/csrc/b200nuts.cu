@@ -1033,9 +1033,12 @@ static int batch_eval(b200_model* m, int C, const double* Q, double* G, double* 
         default: rc = launch_logistic<16>(m, C, Q, ld, bs, st); break;
     }
     if (rc) return rc;
-    logistic_finish_kernel<<<(C + 3) / 4, 128, 0, st>>>(Q, ld, G, ld, n, m->KP, C, bs.cpad, bs.gpart.as<double>(),
-                                                        bs.lpart.as<double>(), gx, logp,
-                                                        m->precision == B200_PRECISION_TC_FP16X2 ? 1 : 0);
+    if (m->precision == B200_PRECISION_TC_FP16X2)  // feature-major partials: the coalesced reduction
+        logistic_finish_fm_kernel<<<dim3((C + 31) / 32, (m->KP + 15) / 16), 256, 0, st>>>(Q, ld, G, ld, n, m->KP, C, bs.cpad, bs.gpart.as<double>(),
+                                                                                         bs.lpart.as<double>(), gx, logp);
+    else
+        logistic_finish_kernel<<<(C + 3) / 4, 128, 0, st>>>(Q, ld, G, ld, n, m->KP, C, bs.cpad, bs.gpart.as<double>(),
+                                                            bs.lpart.as<double>(), gx, logp, 0);
     CU(cudaGetLastError());
     if (launches) *launches += 2;
     return 0;

@@ -309,4 +309,61 @@ __global__ void __launch_bounds__(128) logistic_finish_kernel(const double* __re
     }
 }
 
+// The same reduction for FEATURE-major partials Gpart[p][k][c] (the tensor-core kernels' layout: chains contiguous).  The
+// kernel above walks them with lane = feature, i.e. with a stride of Cpad doubles (measured: 74 us per 512-chain batch, 16 % of
+// the tensor-core lock-step loop, profiles/r2l_launches_logistic_tc_summary.csv).  Here a CTA owns a 32-chain x 16-feature tile:
+// lane = chain while summing (coalesced, 4 independent partial loads in flight per thread, the same fixed order over p as
+// above, so the same bits), a shared-memory transpose for the row-major gradient, and the blockIdx.y == 0 CTAs also produce
+// logp with the arithmetic of the kernel above.
+__global__ void __launch_bounds__(256) logistic_finish_fm_kernel(const double* __restrict__ Q, long long ldq, double* __restrict__ G,
+                                                                 long long ldg, int K, int KP, int C, int Cpad,
+                                                                 const double* __restrict__ Gpart, const double* __restrict__ lpart,
+                                                                 int nparts, double* __restrict__ logp) {
+    __shared__ double tile[16][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // 8 warps: features 2 w, 2 w + 1 of the tile
+    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 16;
+    const int c = c0 + lane;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = k0 + 2 * w + u;
+        double a = 0.0;
+        if (k < KP && c < Cpad) {
+            const double* src = Gpart + (long long)k * Cpad + c;
+            const long long step = (long long)KP * Cpad;
+            int p = 0;
+            for (; p + 4 <= nparts; p += 4) {
+                const double x0 = src[(long long)p * step], x1 = src[(long long)(p + 1) * step];
+                const double x2 = src[(long long)(p + 2) * step], x3 = src[(long long)(p + 3) * step];
+                a += x0; a += x1; a += x2; a += x3;
+            }
+            for (; p < nparts; ++p) a += src[(long long)p * step];
+        }
+        tile[2 * w + u][lane] = a;
+    }
+    __syncthreads();
+    // row-major gradient: thread (cc, kk) of the tile, 16 consecutive features of one chain per half-warp
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+        const int cc = e >> 4, kk = e & 15;
+        const int ch = c0 + cc, k = k0 + kk;
+        if (ch < C && k < K) G[(long long)ch * ldg + k] = tile[kk][cc] - Q[(long long)ch * ldq + k];
+    }
+    if (blockIdx.y == 0) {  // logp of the tile's 32 chains: warp w takes chains w, w + 8, ...
+        for (int cc = w; cc < 32; cc += 8) {
+            const int ch = c0 + cc;
+            if (ch >= C) continue;
+            double s = 0.0;
+            for (int k = lane; k < K; k += 32) {
+                const double b = Q[(long long)ch * ldq + k];
+                s = fma(b, b, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) {
+                double l = 0.0;
+                for (int p = 0; p < nparts; ++p) l += lpart[(long long)p * Cpad + ch];
+                logp[ch] = l - 0.5 * s - K * B200_HALF_LOG_2PI;
+            }
+        }
+    }
+}
+
 }  // namespace b200

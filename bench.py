@@ -610,7 +610,7 @@ def b200_arm(args):
             pass
         roofline = {"bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak,
                     "traffic": None, "peak_source": tsrc,
-                    "kernel": ("logistic_tc_kernel" if args.workload == "logistic" else "gemm_tc_kernel") + " (tcgen05.mma kind::f16, TMEM, TMA)",
+                    "kernel": ("logistic_tc2_kernel" if args.workload == "logistic" else "gemm_tc_kernel") + " (tcgen05.mma kind::f16, TMEM, TMA)",
                     "kernel_ms": k_ms, "algorithmic_flops_per_eval": wl["per_eval"], "issued_tensor_flops_per_eval": 3.0 * wl["per_eval"],
                     "fp64_equivalent_tflops": wl["per_eval"] * per_launch / (k_ms * 1e-3) / 1e12,
                     "accuracy": "gradient <= 1e-6 of its largest entry, logp <= 1e-8 relative vs the fp64 path "

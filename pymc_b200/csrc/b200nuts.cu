@@ -1458,12 +1458,9 @@ extern "C" int b200_nuts_run(b200_model* m, const b200_nuts_cfg* cfg, const doub
         if (run_lockstep(m, Q, st)) return -1;
     } else {
         NutsLaunch L{m, P, st};
-        // Stochastic volatility (n = 3003): a chain can also be spread over 16 warps (6 elements per thread instead of 12).  The
-        // CTA is shared-memory bound either way (one per SM), so 16 warps double the resident warps per SM.  A/B knob:
-        // B200_TEAM_W16=1 / 0 (default: see profiles/r2_variants.md).
-        if (m->kind == B200_MODEL_STOCHVOL && n <= 32 * 16 * 6 && env_int("B200_TEAM_W16", 0) != 0) {
-            if (L.template operator()<StochVolModel, 6, 16>(m->stochvol)) return -1;
-        } else if (dispatch(m, L)) return -1;
+        // (a chain of the stochastic-volatility model spread over 16 warps instead of 8 was measured and rejected: 16.0 M vs
+        // 17.5 M grad-evals/s, the extra cross-warp reduction traffic outweighs the halved per-thread work; profiles/r2_variants.md)
+        if (dispatch(m, L)) return -1;
     }
 
     const double tr_run = trace ? since(tr1) : 0.0;

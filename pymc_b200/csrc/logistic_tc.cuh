@@ -651,16 +651,30 @@ __global__ void __launch_bounds__(kTc2Threads, 1)
                 }
                 // GEMM 2 of the previous slab (it ran under the arithmetic above) frees r; every kTcDrain slabs its accumulator
                 // goes to the fp64 registers first
+                const bool drain_now = (j == 0 && s > 0 && s % kTcDrain == 0);
                 if (j == 0 && s > 0) {
-                    if (s % kTcDrain == 0) drain();
-                    else {
-                        tc_mbar_wait(r_empty, (uint32_t)((s - 1) & 1));
-                        tc_fence_after();
-                    }
+                    if (drain_now) tc_mbar_wait(g_full, (uint32_t)(n_drains & 1));  // GEMM 2 of slab s-1 done: r free, D2 complete
+                    else tc_mbar_wait(r_empty, (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
                 }
                 // 16 rows -> 8 packed columns of r_hi and of r_lo
                 tc_st8(tRh + lane_addr + quarter * 16 + j * 8, v[0], v[2], v[4], v[6], v[8], v[10], v[12], v[14]);
                 tc_st8(tRl + lane_addr + quarter * 16 + j * 8, v[1], v[3], v[5], v[7], v[9], v[11], v[13], v[15]);
+                if (drain_now) {
+                    // the drain: both TMEM loads first, D2 handed back to the MMA issuer as soon as they have landed; the fp64
+                    // conversions and sums run afterwards, off the GEMM 2 -> GEMM 2 critical path
+                    uint32_t d0[16], d1[16];
+                    tc_ld16(tD2 + lane_addr + quarter * 32, d0);
+                    tc_ld16(tD2 + lane_addr + quarter * 32 + 16, d1);
+                    tc_wait_ld();
+                    ++n_drains;
+                    tc_fence_before();
+                    tc_mbar_arrive(g_empty);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) gacc[k] += (double)__uint_as_float(d0[k]);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) gacc[16 + k] += (double)__uint_as_float(d1[k]);
+                }
             }
             tc_wait_st();
             tc_fence_before();

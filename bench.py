@@ -530,6 +530,8 @@ def b200_arm(args):
         # one untimed call: allocates the pooled pinned output buffers the timed calls reuse
         res_h = cm.nuts_run(q0_p, st_e, tune=tune, draws=draws, mean0=mean0_p, store_warmup=False,
                             philox_seed=1999, device_outputs=False, chain_offset=lo, pinned_outputs=True, **run_kw)
+        if world > 1:  # NCCL sets the gather's channels up on its first call (100+ ms): not part of a steady-state step
+            parallel.gather_chains(summary_matrix(res_h.summary), {}, chains_total, dst=0)
         barrier()
         t0 = time.perf_counter()
         ev_tot = 0

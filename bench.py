@@ -121,7 +121,9 @@ def _cpu_chain(job):
     if workload not in _CPU_SPEC:  # built once per worker process
         _CPU_SPEC[workload] = models.BUILDERS[wl["builder"]](**wl["args"])
     spec = _CPU_SPEC[workload]
-    f = logp_numpy.make_logp(spec)
+    # logp/dlogp as COMPILED code where the oracle has a plain-C build (Radon: oracle/c/radon_logp.c, gcc -O3): the reference
+    # evaluates this function as a PyTensor C thunk, so the NumPy form (10x slower per call) would flatter the GPU arm
+    f = logp_numpy.make_logp(spec, compiled=True)
     rng = np.random.default_rng(seed)
     q0 = spec.initial_point() + rng.uniform(-1, 1, spec.n)
     if wl["mass"] == "dense":
@@ -204,6 +206,16 @@ def summary_matrix(summary):
     return np.stack(cols, axis=1)
 
 
+def cpu_logp_kind(workload):
+    from oracle import logp_numpy
+    from pymc_b200 import models
+
+    wl = WORKLOADS[workload]
+    if wl["builder"] == "radon" and os.path.isfile(logp_numpy.RadonLogpC.LIB):
+        return "compiled C (oracle/c/radon_logp.c, gcc -O3) under the Python NUTS of oracle/nuts_numpy.py"
+    return "NumPy/SciPy (oracle/logp_numpy.py) under the Python NUTS of oracle/nuts_numpy.py"
+
+
 def make_pool(procs):
     import multiprocessing as mp
 
@@ -244,7 +256,8 @@ def cpu_measure(args, steps, warm=True):
     eff = rate / (solo_rate * procs)
     info = {"processes": procs, "blas_threads": threads, "physical_cores": len(physical_cpus()), "logical_cpus": host_cores(),
             "pinned": True, "per_core_evals_per_s": rate / procs, "single_core_evals_per_s": solo_rate,
-            "linear_expectation": solo_rate * procs, "parallel_efficiency": eff}
+            "linear_expectation": solo_rate * procs, "parallel_efficiency": eff,
+            "logp": cpu_logp_kind(args.workload)}
     if eff < 0.5:
         info["warning"] = (f"host delivers {eff:.0%} of linear scaling over {procs} pinned processes: the CPU arm is "
                            "memory/SMT/cgroup bound on this box; compare with linear_expectation")

@@ -21,6 +21,8 @@ Only tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() may import 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 LOG_2PI = np.log(2.0 * np.pi)
@@ -225,6 +227,43 @@ _BY_KIND = {
 }
 
 
-def make_logp(spec):
-    """ModelSpec -> callable q -> (logp, grad)."""
+class RadonLogpC:
+    """The same function as ``RadonLogp`` from oracle/c/radon_logp.c (gcc -O3, built by ``make -C oracle/c`` /
+    ``__graft_entry__.build()``): what bench.py's CPU baseline calls, so that a logp/dlogp evaluation costs what compiled code
+    costs -- the reference runs this function as a PyTensor C thunk (model/core.py:232-267)."""
+
+    LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libradon_logp.so")
+
+    def __init__(self, spec):
+        import ctypes as C
+
+        lib = C.CDLL(self.LIB)
+        fn = lib.radon_logp_dlogp
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._fn = fn
+        self.idx = np.ascontiguousarray(spec.data["county_idx"], dtype=np.int64)
+        self.x = np.ascontiguousarray(spec.data["floor"], dtype=np.float64)
+        self.y = np.ascontiguousarray(spec.data["y"], dtype=np.float64)
+        self.J, self.n, self.N = int(spec.meta["n_counties"]), spec.n, len(self.y)
+        self._Ga, self._Gb = np.empty(self.J), np.empty(self.J)
+        self._args = (self.J, self.N, self.idx.ctypes.data, self.x.ctypes.data, self.y.ctypes.data)
+        self._scr = (self._Ga.ctypes.data, self._Gb.ctypes.data)
+
+    def __call__(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        g = np.empty(self.n)
+        lp = self._fn(q.ctypes.data, *self._args, g.ctypes.data, *self._scr)
+        return float(lp), g
+
+
+def compiled_logp_available(spec) -> bool:
+    return spec.name == "radon" and os.path.isfile(RadonLogpC.LIB)
+
+
+def make_logp(spec, compiled: bool = False):
+    """ModelSpec -> callable q -> (logp, grad).  ``compiled=True``: the plain-C build where one exists (Radon), for the CPU
+    baseline; parity tests and goldens use the NumPy forms."""
+    if compiled and compiled_logp_available(spec):
+        return RadonLogpC(spec)
     return _BY_KIND[spec.kind](spec)

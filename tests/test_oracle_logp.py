@@ -123,3 +123,30 @@ def test_model_dlogp_closed_form():
     lp, g = f(np.array([0.0, 1.0, -2.0]))
     np.testing.assert_allclose(g, [0.0, -1.0, 2.0])
     assert lp == pytest.approx(st.norm.logpdf([0.0, 1.0, -2.0]).sum())
+
+
+def test_compiled_radon_logp_equals_the_numpy_form():
+    """oracle/c/radon_logp.c (the compiled-code logp of bench.py's CPU baseline) against RadonLogp, logp and gradient."""
+    import os
+    import shutil
+    import subprocess
+
+    from oracle import logp_numpy
+    from pymc_b200 import models
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile(logp_numpy.RadonLogpC.LIB):
+        if shutil.which("gcc") is None or shutil.which("make") is None:
+            pytest.skip("no C toolchain to build oracle/c")
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle", "c")])
+    spec = models.radon()
+    f, fc = logp_numpy.make_logp(spec), logp_numpy.make_logp(spec, compiled=True)
+    assert type(fc).__name__ == "RadonLogpC"
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        q = spec.initial_point() + rng.uniform(-2, 2, spec.n)
+        a, ga = f(q)
+        b, gb = fc(q)
+        assert abs(a - b) <= 1e-12 * abs(a) and np.max(np.abs(ga - gb)) <= 1e-12 * np.max(np.abs(ga))
+    # models without a C build fall back to the NumPy form
+    assert type(logp_numpy.make_logp(models.eight_schools(), compiled=True)).__name__ == "EightSchoolsLogp"

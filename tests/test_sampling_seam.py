@@ -56,6 +56,29 @@ def test_chains_are_the_reference_chains_for_their_streams():
         assert np.array_equal(qs[tune:], res.unconstrained[c])
 
 
+def test_init_adapt_full_hands_the_reference_potential_to_the_engine():
+    """init="jitter+adapt_full" (mcmc.py:1997-2005): QuadPotentialFullAdapt(n, mean of the start points, eye, 10) per chain."""
+    from oracle import logp_numpy, nuts_numpy
+    from pymc_b200 import rng as brng
+
+    spec = models.eight_schools()
+    chains, seed, tune, draws = 2, 8, 25, 6
+    res = sampling.sample_b200_nuts(draws, tune=tune, chains=chains, random_seed=seed, model=OracleEngine(spec), momentum="numpy",
+                                    keep_untransformed=True, init="jitter+adapt_full")
+    step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(seed, chains)
+    q0 = sampling.initial_points(spec, chains, jitter_seeds)
+    f = logp_numpy.make_logp(spec)
+    for c in range(chains):
+        o = nuts_numpy.Oracle(f, nuts_numpy.DenseAdaptMass(spec.n, q0.mean(axis=0), np.eye(spec.n), 10))
+        o.rng, o.mass.rng = step_rngs[c], pot_rngs[c]
+        qs, _ = o.run(q0[c], tune, draws)
+        assert np.array_equal(qs[tune:], res.unconstrained[c])
+    import pytest
+
+    with pytest.raises(ValueError, match="adapt_full"):
+        sampling.sample_b200_nuts(2, tune=2, chains=1, random_seed=1, model=OracleEngine(spec), momentum="numpy", init="advi")
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys

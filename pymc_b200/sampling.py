@@ -53,10 +53,11 @@ class SampleResult:
     attrs: dict = field(default_factory=dict)
     observed_data: dict = field(default_factory=dict)   # groups external samplers are held to (test_mcmc_external.py:78-85)
     constant_data: dict = field(default_factory=dict)
+    log_likelihood: dict = field(default_factory=dict)  # observed rv name -> [chains, draws, N] (idata_kwargs["log_likelihood"])
 
     def groups(self):
         out = ["posterior", "sample_stats"]
-        out += [g for g in ("observed_data", "constant_data") if getattr(self, g)]
+        out += [g for g in ("log_likelihood", "observed_data", "constant_data") if getattr(self, g)]
         out += [g for g in ("warmup_posterior", "warmup_sample_stats") if getattr(self, g) is not None]
         return out
 
@@ -64,7 +65,22 @@ class SampleResult:
         import arviz as az  # optional
 
         return az.from_dict(posterior=self.posterior, sample_stats=self.sample_stats, observed_data=self.observed_data or None,
-                            constant_data=self.constant_data or None, attrs=self.attrs)
+                            constant_data=self.constant_data or None, log_likelihood=self.log_likelihood or None, attrs=self.attrs)
+
+
+def _log_likelihood(cm, dq):
+    """The `log_likelihood` group (sampling/jax.py:128-144, :660-673; pm.compute_log_likelihood, stats/log_density.py:31-77):
+    log p(y_i | draw) for every likelihood factor of the model's IR, evaluated on the device by the generic IR function
+    (``b200_pointwise_loglik``).  ``dq``: unconstrained draws [chains, draws, n]."""
+    ir = getattr(cm, "ir", None)
+    if ir is None or not hasattr(cm, "pointwise_loglik"):
+        raise NotImplementedError("idata_kwargs={'log_likelihood': True} needs a model given as pymc_b200.ir.ModelIR (from_pymc)")
+    eng = cm
+    if getattr(cm.spec, "name", "ir") != "ir":  # the model runs on a hand-specialised kernel: the pointwise pass is the generic one
+        eng = cm.__dict__.get("_generic_engine")
+        if eng is None:
+            eng = cm.__dict__["_generic_engine"] = CompiledModel(ir, device=getattr(cm, "device", None), specialise=False)
+    return {L.name: eng.pointwise_loglik(np.asarray(dq), lik=i) for i, L in enumerate(ir.likelihoods)}
 
 
 def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, jitter=True, logp_fn=None,
@@ -146,6 +162,7 @@ def sample_b200_nuts(
     Multi-GPU (torch.distributed initialised, one process per GPU): chains are sharded over the ranks; ``gather="rank0"``
     collects all chains on rank 0 (the other ranks return their own shard, ``attrs["chains_held"]`` says which),
     ``"all"`` gives every rank everything (world-size times the traffic), ``"none"`` leaves the posterior sharded.
+    ``idata_kwargs={"log_likelihood": True}`` adds the pointwise log-likelihood group (IR models; evaluated on the device).
     Posterior values are constrained ON THE DEVICE where each draw is recorded (the backward transform is fused into the
     kernel); ``keep_untransformed=True`` records the unconstrained positions and transforms on the host instead.
     """
@@ -194,7 +211,8 @@ def sample_b200_nuts(
     # Philox key of the device momentum noise: an independent child of the root seed (never a function of a chain's jitter)
     seed_key = brng.philox_key(random_seed) if z is None else 0
     # draws recorded in constrained space by the kernel itself (engines that implement `constrain`; test stand-ins do not)
-    on_device = (not keep_untransformed) and getattr(cm, "supports_constrain", False)
+    want_ll = bool((idata_kwargs or {}).get("log_likelihood", False))  # needs the unconstrained draws on the host
+    on_device = (not keep_untransformed) and getattr(cm, "supports_constrain", False) and not want_ll
     if on_device:
         nk["constrain"] = True
 
@@ -234,6 +252,8 @@ def sample_b200_nuts(
         obs = {"y"}
         out.observed_data = {k: np.asarray(v) for k, v in spec.data.items() if k in obs}
         out.constant_data = {k: np.asarray(v) for k, v in spec.data.items() if k not in obs and np.ndim(v) == 1}
+    if want_ll:
+        out.log_likelihood = _log_likelihood(cm, d_all[:, w:])
     if w:
         out.warmup_posterior, out.warmup_sample_stats = pack(d_all[:, :w], {k: v[:, :w] for k, v in st_all.items()})
     out.attrs = {"sampling_time": sampling_time, "tuning_steps": tune, "inference_library": "pymc_b200", "chains_held": held,

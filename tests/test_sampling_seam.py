@@ -79,6 +79,45 @@ def test_init_adapt_full_hands_the_reference_potential_to_the_engine():
         sampling.sample_b200_nuts(2, tune=2, chains=1, random_seed=1, model=OracleEngine(spec), momentum="numpy", init="advi")
 
 
+def test_log_likelihood_group_from_the_pointwise_pass():
+    """idata_kwargs={"log_likelihood": True} (sampling/jax.py:660-673): the sampler records unconstrained draws and asks the
+    engine's pointwise pass for log p(y_i | draw) of every likelihood factor; here the engine is the oracle-backed stand-in."""
+    from scipy import stats as st
+
+    from oracle import ir_numpy
+    from pymc_b200 import engine, ir
+
+    m = ir.radon_ir(60, 5, 3)
+
+    class IrStandIn(OracleEngine):
+        def __init__(self, model):
+            self.ir, self.spec = model, engine._ir_spec(model)
+            self.n, self.f = model.n, ir_numpy.make_logp(model)
+            self.calls = []
+
+        def pointwise_loglik(self, draws, lik=0):
+            self.calls.append((np.shape(draws), lik))
+            c = self.ir.constrain(np.asarray(draws))
+            L = self.ir.likelihoods[lik]
+            county, floor = L.terms[1].factors[1][1], L.terms[2].coef
+            mu = (c["mu_a"][..., None] + c["sigma_a"][..., None] * c["a"][..., county]
+                  + (c["mu_b"][..., None] + c["sigma_b"][..., None] * c["b"][..., county]) * floor)
+            return st.norm(mu, c["eps"][..., None]).logpdf(L.y)
+
+    eng = IrStandIn(m)
+    res = sampling.sample_b200_nuts(5, tune=8, chains=2, random_seed=4, model=eng, momentum="numpy",
+                                    idata_kwargs={"log_likelihood": True}, compute_convergence_checks=False)
+    name = m.likelihoods[0].name
+    assert "log_likelihood" in res.groups() and set(res.log_likelihood) == {name}
+    assert res.log_likelihood[name].shape == (2, 5, 60) and eng.calls == [((2, 5, m.n), 0)]
+    assert np.all(np.isfinite(res.log_likelihood[name])) and np.all(res.posterior["eps"] > 0)
+    plain = sampling.sample_b200_nuts(5, tune=8, chains=2, random_seed=4, model=IrStandIn(m), momentum="numpy",
+                                      compute_convergence_checks=False)
+    assert "log_likelihood" not in plain.groups()
+    for k in res.posterior:  # asking for the group does not change the draws
+        assert np.array_equal(res.posterior[k], plain.posterior[k])
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys

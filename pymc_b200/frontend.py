@@ -9,7 +9,8 @@ pymc/model/fgraph.py:76-81, :139) -- and pattern-matches them onto the closed fa
     free RV      ->  ir.Var (transform from rvs_to_transforms) + ir.Prior (parameters: constants or scalar free RVs),
                      AR(1) / GaussianRandomWalk -> ir.AR1
     observed RV  ->  ir.Likelihood; its location parameter is parsed into linear-predictor terms
-                     (Add / Sub / Neg / Mul / indexing by constant integer arrays / Dot with a constant matrix / broadcasts)
+                     (Add / Sub / Neg / Mul / division by a constant / indexing by constant integer arrays / Dot with a
+                     constant matrix / broadcasts); Normal(0, exp(eta / 2)) with a linear eta -> the log-variance likelihood
 
 Anything outside the closed set raises ``NotImplementedError`` naming the offending op, so a model either lowers exactly
 or not at all.  PyMC and PyTensor are NOT importable in the build image; this module imports them lazily and
@@ -195,6 +196,13 @@ def from_pymc(model) -> _ir.ModelIR:
             return terms_of(a, N) + [(-1.0 * c if np.ndim(c) == 0 else -c, f) for c, f in terms_of(b, N)]
         if son == "neg":
             return [(-1.0 * c if np.ndim(c) == 0 else -c, f) for c, f in terms_of(node.inputs[0], N)]
+        if son in ("truediv", "true_div"):  # (linear predictor) / constant
+            a, b = node.inputs
+            d = _const_value(b)
+            if d is None:
+                raise NotImplementedError("linear predictor: division by a non-constant")
+            d = np.broadcast_to(np.asarray(d, dtype=np.float64), (N,)).copy() if d.size > 1 else float(d.reshape(()))
+            return [(c / d, f) for c, f in terms_of(a, N)]
         if son == "mul":
             acc = [(1.0, [])]
             for inp in node.inputs:
@@ -240,6 +248,17 @@ def from_pymc(model) -> _ir.ModelIR:
             return param(s, rv.name + ".sigma")
 
         if op == "normal":
+            # the stochastic-volatility observation y ~ Normal(0, exp(c * eta)) with a linear eta (c = 1/2: eta is the log-variance)
+            log_sd, loc0 = ps[1], _const_value(ps[0])
+            while log_sd.owner is not None and isinstance(log_sd.owner.op, DimShuffle):
+                log_sd = log_sd.owner.inputs[0]
+            log_sd = strip(log_sd, "exp")
+            if log_sd is not None and loc0 is not None and not np.any(loc0):
+                doubled = [(2.0 * c, f) for c, f in terms_of(log_sd, N)]  # eta = 2 log sd
+                terms = [_ir.Term(list(f), None if (np.ndim(c) == 0 and float(c) == 1.0) else
+                                  (np.asarray(c, dtype=np.float64) if np.ndim(c) else float(c))) for c, f in doubled]
+                liks.append(_ir.Likelihood("normal_logvar", y, terms, name=rv.name))
+                continue
             liks.append(_ir.Likelihood("normal", y, make_terms(ps[0], N), sigma=sigma_of(ps[1]), name=rv.name))
         elif op == "studentt":
             nu = _const_value(ps[0])

@@ -235,6 +235,45 @@ def test_hierarchical_logistic_graph_with_dot_and_shared_data(fake_pytensor):
     np.testing.assert_allclose(dlp, num, rtol=1e-5, atol=1e-6)
 
 
+class IntervalTransform:
+    def __init__(self, lo, hi):
+        self._b = (lo, hi)
+
+    def args_fn(self, *inputs):
+        return self._b
+
+
+def test_stochastic_volatility_graph_ar1_interval_and_log_variance_likelihood(fake_pytensor):
+    """BASELINE config 4 as a PyMC graph: mu ~ Normal(0, 5), phi ~ Uniform(-1, 1) (interval transform), sigma ~ Exponential(10)
+    (PyTensor's scale parametrisation), h ~ AR(rho=[phi], sigma, init_dist=Normal(0, 1)), y ~ Normal(0, exp((mu + h) / 2))."""
+    from oracle import logp_numpy
+    from pymc_b200 import from_pymc, models
+
+    spec = models.stochvol(T=40, seed=4)
+    y = spec.data["y"]
+    T = len(y)
+    M = FakeModel("stochvol")
+    mu = M.free(rv("NormalRV", "mu", Constant(0.0), Constant(5.0)), 1)
+    lo, hi = Constant(-1.0), Constant(1.0)
+    phi = rv("UniformRV", "phi", lo, hi)
+    M.free(phi, 1, IntervalTransform(lo, hi))
+    M.rvs_to_values[phi].name = "phi_interval__"
+    M._ip["phi_interval__"] = M._ip.pop("phi_log__")
+    sigma = M.free(rv("ExponentialRV", "sigma", Constant(0.1)), 1, LogTransform(), initial=[np.log(0.1)])
+    init = rv("NormalRV", "init", Constant(0.0), Constant(1.0))
+    ar_op = type("AutoRegressiveRV", (), {"ar_order": 1, "constant_term": False,
+                                          "dist_params": lambda self, node: node.inputs[2:]})()
+    h = apply(ar_op, Variable("rng"), Constant(np.array([])), apply(DimShuffle(), phi), bcast(sigma), init, name="h")
+    M.free(h, T)
+    log_sd = elem("TrueDiv", elem("Add", bcast(mu), h), Constant(2.0))
+    M.observe(rv("NormalRV", "y", Constant(0.0), elem("Exp", log_sd)), y)
+    m = from_pymc(M)
+    assert [v.name for v in m.vars] == ["mu", "phi_interval__", "sigma_log__", "h"] and m.n == spec.n
+    assert m.vars[1].transform == "interval" and m.vars[1].bounds == (-1.0, 1.0)
+    assert m.likelihoods[0].dist == "normal_logvar" and len(m.ar1) == 1
+    _same_density(m, logp_numpy.make_logp(spec), spec.n, seed=3)
+
+
 def test_graphs_outside_the_closed_set_are_refused(fake_pytensor):
     from pymc_b200 import from_pymc
 

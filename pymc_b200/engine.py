@@ -56,13 +56,13 @@ class CompiledModel:
     a hand-specialised kernel when ``ir.specialise`` recognises its shape, otherwise evaluated by the generic IR device
     function) or a ``models.ModelSpec`` naming one of the hand-written kernels directly (the GEMM-shaped configs)."""
 
-    def __init__(self, spec, device: int | None = None, specialise: bool = True):
+    def __init__(self, spec, device: int | None = None, specialise: bool | str = True):
         from . import ir as _ir
 
         self.ir = None
         if isinstance(spec, _ir.ModelIR):
             self.ir = spec
-            fast = _ir.specialise(spec) if specialise else None
+            fast = _ir.specialise(spec, extended=(specialise == "all")) if specialise else None
             spec = fast if fast is not None else _ir_spec(spec)
         self.spec = spec
         self.n = spec.n

@@ -365,23 +365,81 @@ def lower(ir: ModelIR) -> LoweredIR:
 # ------------------------------------------------------------------------------------------------------------------------
 # pattern -> hand-specialised kernel (fast paths behind the IR)
 # ------------------------------------------------------------------------------------------------------------------------
-def specialise(ir: ModelIR):
+def specialise(ir: ModelIR, extended: bool = False):
     """Return a ``models.ModelSpec`` of a hand-written kernel when the IR is one of the recognised shapes, else None.
 
-    Recognised: the non-centred varying-intercept/varying-slope Normal regression of benchmarks.py:34-45 (Radon; any data)
-    and non-centred Eight Schools (any J).  Everything else runs on the generic IR device function."""
+    Recognised: the non-centred varying-intercept/varying-slope Normal regression of benchmarks.py:34-45 (Radon; any data),
+    non-centred Eight Schools (any J), the AR(1) stochastic-volatility model of BASELINE config 4 (any T) and the logistic GLM
+    of config 3 (beta ~ Normal(0, 1), up to 128 features: the fused design-matrix kernels, fp64 DMMA or tcgen05) -- these two
+    only with ``extended=True`` (``CompiledModel(ir, specialise="all")``): the routes were added after the round's last GPU run
+    and are checked on the CPU only (the specialised spec has the IR's density, tests/test_ir.py), so the default keeps such
+    models on the generic function.  Everything else runs on the generic IR device function."""
     from . import models
 
     def const(p, k, want=None):
         return not isinstance(p.params[k], Ref) and (want is None or float(p.params[k]) == want)
 
     pri = {ir.var(p.var).name: p for p in ir.priors}
-    if len(pri) != len(ir.priors) or ir.ar1 or len(ir.likelihoods) != 1:
+    if len(pri) != len(ir.priors) or len(ir.likelihoods) != 1:
         return None
     L = ir.likelihoods[0]
     names = [v.name for v in ir.vars]
     tr = [v.transform for v in ir.vars]
     sizes = [v.size for v in ir.vars]
+
+    def plain(t, vn):  # the term is exactly the variable: no coefficient, no gather index
+        return t.coef is None and len(t.factors) == 1 and t.factors[0][0] == vn and t.factors[0][1] is None
+
+    # ---- stochastic volatility (BASELINE config 4): [mu, phi (interval -1, 1), log sigma, h[T]] ------------------------
+    if extended and len(ir.ar1) == 1 and L.dist == "normal_logvar":
+        A = ir.ar1[0]
+        if not (len(names) == 4 and tr == [None, "interval", "log", None] and sizes[:3] == [1, 1, 1] and sizes[3] == len(L.y)
+                and tuple(ir.vars[1].bounds or ()) == (-1.0, 1.0) and len(pri) == 3 and L.sigma is None and len(L.terms) == 2):
+            return None
+        mu, phi, sg, h = names
+        ok = (ir.var(A.var).name == h and isinstance(A.phi, Ref) and ir.var(A.phi.var).name == phi
+              and isinstance(A.sigma, Ref) and ir.var(A.sigma.var).name == sg and float(A.init_sigma) == 1.0
+              and plain(L.terms[0], mu) and plain(L.terms[1], h)
+              and mu in pri and pri[mu].dist == "normal" and const(pri[mu], 0, 0.0) and const(pri[mu], 1, 5.0)
+              and phi in pri and pri[phi].dist == "uniform" and const(pri[phi], 0, -1.0) and const(pri[phi], 1, 1.0)
+              and sg in pri and pri[sg].dist == "exponential" and const(pri[sg], 0, 10.0))
+        if not ok:
+            return None
+        spec = models.stochvol(T=4)  # layout donor; data and sizes replaced below
+        T = len(L.y)
+        spec.n = T + 3
+        spec.vars, _ = models._layout([(v.name, v.rv_name, v.size, v.transform, v.bounds) for v in ir.vars])
+        spec.data = {"y": np.asarray(L.y, dtype=np.float64)}
+        spec.meta = {"T": T, "initial_point": ir.initial_point()}
+        return spec
+    if ir.ar1:
+        return None
+    # ---- logistic GLM (BASELINE config 3): beta ~ Normal(0, 1)^K, y ~ Bernoulli(logit_p = X beta), K <= 128 --------------
+    if extended and L.dist == "bernoulli_logit":
+        if not (len(names) == 1 and tr == [None] and 1 <= sizes[0] <= 128 and len(L.terms) == sizes[0]):
+            return None
+        beta, K, N = names[0], sizes[0], len(L.y)
+        if not (beta in pri and pri[beta].dist == "normal" and const(pri[beta], 0, 0.0) and const(pri[beta], 1, 1.0)):
+            return None
+        if not np.all((np.asarray(L.y) == 0) | (np.asarray(L.y) == 1)):
+            return None
+        X = np.empty((N, K))
+        seen = set()
+        for t in L.terms:
+            if len(t.factors) != 1 or t.factors[0][0] != beta or t.factors[0][1] is None or np.ndim(t.coef) != 1 or len(t.coef) != N:
+                return None
+            ix = np.asarray(t.factors[0][1])
+            k = int(ix[0])
+            if k in seen or not (0 <= k < K) or not np.all(ix == k):
+                return None
+            seen.add(k)
+            X[:, k] = t.coef
+        spec = models.logistic(n_rows=4, n_features=2)  # layout donor
+        spec.n = K
+        spec.vars, _ = models._layout([(beta, ir.vars[0].rv_name, K, None, None)])
+        spec.data = {"X": X, "y": np.asarray(L.y).astype(np.uint8)}
+        spec.meta = {"n_rows": N, "initial_point": ir.initial_point()}
+        return spec
     if L.dist != "normal":
         return None
     # ---- Eight Schools: [mu, log tau, theta_t[J]] ---------------------------------------------------------------

@@ -124,6 +124,46 @@ def test_specialise_routes_recognised_shapes_to_the_hand_written_kernels():
     assert ir.specialise(ir.stochvol_ir(T=50)) is None and ir.specialise(ir.varying_intercept_logistic_ir()) is None
 
 
+def test_extended_specialisation_routes_configs_3_and_4_to_their_hand_kernels():
+    """specialise(extended=True): the AR(1) stochastic-volatility IR -> the StochVol kernel's ModelSpec, a Bernoulli-logit GLM with
+    beta ~ Normal(0, 1) -> the fused design-matrix kernels' ModelSpec; the specialised spec has the IR's density and gradient
+    (NumPy restatements of both), anything that deviates stays on the generic function."""
+    from oracle import ir_numpy, logp_numpy
+
+    m = ir.stochvol_ir(T=50)
+    sv = ir.specialise(m, extended=True)
+    ref = models.stochvol(T=50)
+    assert sv is not None and sv.name == "stochvol" and sv.n == ref.n and np.array_equal(sv.data["y"], ref.data["y"])
+    assert np.array_equal(sv.initial_point(), ref.initial_point()) and [v.name for v in sv.vars] == [v.name for v in ref.vars]
+    f_ir, f_spec = ir_numpy.make_logp(m), logp_numpy.make_logp(sv)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        q = m.initial_point() + rng.uniform(-0.5, 0.5, m.n)
+        (a, ga), (b, gb) = f_ir(q), f_spec(q)
+        assert abs(a - b) <= 1e-11 * abs(b) and np.max(np.abs(ga - gb)) <= 1e-10 * np.max(np.abs(gb))
+    off = ir.stochvol_ir(T=50)
+    off.ar1[0] = ir.AR1("h", ir.Ref("phi_interval__"), ir.Ref("sigma_log__"), 2.0)  # another init_dist: not the kernel's model
+    assert ir.specialise(off, extended=True) is None
+    # logistic GLM written as K coefficient columns (what from_pymc produces for dot(X, beta))
+    lg = models.logistic(n_rows=300, n_features=5, seed=2)
+    X, y = lg.data["X"], lg.data["y"].astype(np.float64)
+    terms = [ir.Term([("beta", np.full(300, k, dtype=np.int32))], coef=X[:, k].copy()) for k in range(5)]
+    g = ir.ModelIR(vars=[ir.Var("beta", "beta", 5)], priors=[ir.Prior("normal", "beta", (0.0, 1.0))],
+                   likelihoods=[ir.Likelihood("bernoulli_logit", y, terms)])
+    g.validate()
+    assert ir.specialise(g) is None
+    sp = ir.specialise(g, extended=True)
+    assert sp is not None and sp.name == "logistic" and sp.n == 5 and np.array_equal(sp.data["X"], X)
+    assert sp.data["y"].dtype == np.uint8 and np.array_equal(sp.data["y"], lg.data["y"])
+    f_ir, f_spec = ir_numpy.make_logp(g), logp_numpy.make_logp(sp)
+    for _ in range(3):
+        q = rng.uniform(-1, 1, 5)
+        (a, ga), (b, gb) = f_ir(q), f_spec(q)
+        assert abs(a - b) <= 1e-11 * abs(b) and np.max(np.abs(ga - gb)) <= 1e-10 * np.max(np.abs(gb))
+    g.priors[0] = ir.Prior("normal", "beta", (0.0, 2.5))
+    assert ir.specialise(g, extended=True) is None
+
+
 def test_validation_rejects_what_is_outside_the_closed_set():
     v = [ir.Var("x", "x", 3)]
     with pytest.raises(ValueError):

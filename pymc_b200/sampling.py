@@ -151,7 +151,8 @@ def sample_b200_nuts(
     Arguments follow ``sample_jax_nuts`` (pymc/sampling/jax.py:495-517).  ``model``: a ``pymc_b200.ir.ModelIR`` (any model
     of the closed factor set; ``from_pymc`` lowers a ``pm.Model`` to one), a ``ModelSpec`` naming a hand-written kernel, or
     a ``CompiledModel``.  ``nuts_kwargs`` accepts the ``pm.NUTS`` / ``pm.HamiltonianMC`` keywords ``max_treedepth,
-    early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size, path_length, max_steps``.
+    early_max_treedepth, step_scale, gamma, k, t0, Emax, adapt_step_size, path_length, max_steps`` and ``potential`` (one of the
+    reference's ``QuadPotential*`` objects: read and mapped onto the engine's mass kinds, ``pymc_b200.potentials``).
     ``init`` (pm.sample / init_nuts, pymc/sampling/mcmc.py:1759-2021): "auto" = "jitter+adapt_diag"; "adapt_diag";
     "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250);
     "adapt_full" / "jitter+adapt_full" (QuadPotentialFullAdapt: a dense covariance per chain, identity start, weight 10,
@@ -198,6 +199,23 @@ def sample_b200_nuts(
         raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag, (jitter+)adapt_diag_grad and "
                          "(jitter+)adapt_full")
     mass = nk.pop("mass", mass)  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
+    # pm.NUTS(potential=...) (hmc/base_hmc.py:82-169): a reference QuadPotential object replaces init's mass matrix
+    pot_var0 = pot_mean0 = None
+    potential = nk.pop("potential", None)
+    if potential is not None:
+        from . import potentials
+
+        pk = potentials.engine_kwargs(potential, spec.n)
+        mass = pk.pop("mass")
+        pot_var0, pot_mean0 = pk.pop("var0", None), pk.pop("mean0", None)
+        if "dense_cov" in pk:
+            cm.set_dense_mass(cov=pk.pop("dense_cov"))
+        elif "dense_inverse" in pk:
+            cm.set_dense_mass(inverse=pk.pop("dense_inverse"))
+        for k_, v_ in pk.items():
+            if k_ in nk and nk[k_] != v_:
+                raise ValueError(f"nuts_kwargs[{k_!r}] contradicts the potential object ({nk[k_]!r} vs {v_!r})")
+            nk[k_] = v_
 
     from . import parallel
 
@@ -205,7 +223,9 @@ def sample_b200_nuts(
     step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(random_seed, chains)
     q0_all = initial_points(spec, chains, jitter_seeds, initvals, jitter, cm.logp_dlogp)
     # init_nuts: mean start point over ALL chains as the estimator's prior mean (mcmc.py:1890-1894)
-    mean0 = np.broadcast_to(q0_all.mean(axis=0), (hi - lo, spec.n)).copy()
+    mean0 = np.broadcast_to(q0_all.mean(axis=0) if pot_mean0 is None else pot_mean0, (hi - lo, spec.n)).copy()
+    if pot_var0 is not None:
+        nk["var0"] = np.broadcast_to(pot_var0, (hi - lo, spec.n)).copy()
     states = brng.pack_pcg64(step_rngs[lo:hi])
     z = brng.momentum_noise(pot_rngs[lo:hi], tune + draws, spec.n) if momentum == "numpy" else None
     # Philox key of the device momentum noise: an independent child of the root seed (never a function of a chain's jitter)

@@ -134,7 +134,7 @@ class OracleEngine:
         from oracle import nuts_numpy
         from pymc_b200.engine import NutsResult
 
-        assert mass in ("diag_adapt", "dense_adapt") and z is not None, "the stand-in draws momentum from the host stream only"
+        assert mass in ("diag", "diag_adapt", "dense_adapt") and z is not None, "the stand-in draws momentum from the host stream only"
         q0 = np.asarray(q0, dtype=np.float64).reshape(-1, self.n)
         C, T = q0.shape[0], tune + draws
         qs_all, st_all = [], []
@@ -144,8 +144,12 @@ class OracleEngine:
             if mass == "dense_adapt":  # QuadPotentialFullAdapt(n, mean, diag(var0), weight): init="adapt_full"
                 m = nuts_numpy.DenseAdaptMass(self.n, m0.copy(), np.diag(v0), mass_initial_weight,
                                               adaptation_window=unused.get("adaptation_window", 101))
+            elif mass == "diag":  # QuadPotentialDiag(v)
+                m = nuts_numpy.DiagMass(v0, adapt=False)
             else:
-                m = nuts_numpy.DiagMass(v0, adapt=True, initial_mean=m0.copy(), initial_weight=mass_initial_weight)
+                m = nuts_numpy.DiagMass(v0, adapt=True, initial_mean=m0.copy(), initial_weight=mass_initial_weight,
+                                        adaptation_window=unused.get("adaptation_window", 101),
+                                        discard_window=unused.get("discard_window", 50))
             o = nuts_numpy.Oracle(self.f, m, step_scale=step_scale, adapt_step_size=adapt_step_size, target_accept=target_accept,
                                   gamma=gamma, k=k, t0=t0, Emax=Emax, max_treedepth=max_treedepth,
                                   early_max_treedepth=early_max_treedepth)

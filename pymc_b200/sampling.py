@@ -121,6 +121,34 @@ def initial_points(spec: ModelSpec, chains: int, jitter_seeds, initvals=None, ji
     return q0
 
 
+def map_and_neg_hessian(cm, start, maxeval: int = 5000, rel_step: float = 1e-5):
+    """init="map" (sampling/mcmc.py:1981-1985): ``start = find_MAP()``; ``cov = -find_hessian(start, negate_output=False)``.
+
+    ``find_MAP`` (tuning/starting.py:52-190) minimises ``-logp`` over the unconstrained vector with SciPy's L-BFGS-B using the
+    model's own logp/dlogp, from the initial point, with at most ``maxeval`` evaluations: the same call here, on the engine's
+    ``logp_dlogp``.  The Hessian the reference compiles symbolically (``Model.compile_d2logp``) is taken as central differences
+    of the gradient -- all 2n displaced points in ONE batched device call.  The reference hands ``-H`` to ``QuadPotentialFull``
+    as its covariance, and so does this (the docstring of find_MAP advises against this initialisation; it is here for parity of
+    the ``init`` surface).  Returns (q_map[n], cov[n, n])."""
+    from scipy import optimize
+
+    start = np.asarray(start, dtype=np.float64)
+    n = start.size
+
+    def cost(x):
+        lp, g = cm.logp_dlogp(x[None, :])
+        return -float(lp[0]), -np.asarray(g[0], dtype=np.float64)
+
+    res = optimize.minimize(cost, start, jac=True, method="L-BFGS-B", options={"maxfun": int(maxeval)})
+    q = np.asarray(res.x, dtype=np.float64)
+    h = rel_step * np.maximum(1.0, np.abs(q))
+    pts = np.concatenate([q[None, :] + np.diag(h), q[None, :] - np.diag(h)])
+    _, g = cm.logp_dlogp(pts)
+    H = (np.asarray(g[:n]) - np.asarray(g[n:])) / (2.0 * h)[:, None]
+    H = 0.5 * (H + H.T)
+    return q, -H
+
+
 def sample_b200_nuts(
     draws: int = 1000,
     *,
@@ -156,7 +184,7 @@ def sample_b200_nuts(
     ``init`` (pm.sample / init_nuts, pymc/sampling/mcmc.py:1759-2021): "auto" = "jitter+adapt_diag"; "adapt_diag";
     "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250);
     "adapt_full" / "jitter+adapt_full" (QuadPotentialFullAdapt: a dense covariance per chain, identity start, weight 10,
-    mcmc.py:1986-2005).
+    mcmc.py:1986-2005); "map" (every chain starts at the L-BFGS-B optimum, QuadPotentialFull(-Hessian), mcmc.py:1981-1985).
     ``step``: "nuts" (target_accept default 0.8) or "hmc" (HamiltonianMC, default 0.65).
     ``momentum="numpy"`` draws the momentum normals from each chain's NumPy potential stream exactly like
     the reference (host-generated, uploaded); ``"device"`` generates them on the GPU (Philox).
@@ -195,9 +223,11 @@ def sample_b200_nuts(
         nk.setdefault("stop_adaptation", tune - 50 if tune > 250 else None)  # mcmc.py:1900-1903
     elif init == "adapt_full":
         mass = "dense_adapt"  # QuadPotentialFullAdapt(n, mean, eye, 10): mcmc.py:1986-2005
+    elif init == "map":
+        mass = "dense"        # every chain starts at the MAP; QuadPotentialFull(-Hessian): mcmc.py:1981-1985 (resolved below)
     else:
-        raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag, (jitter+)adapt_diag_grad and "
-                         "(jitter+)adapt_full")
+        raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag, (jitter+)adapt_diag_grad, "
+                         "(jitter+)adapt_full and map")
     mass = nk.pop("mass", mass)  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
     # pm.NUTS(potential=...) (hmc/base_hmc.py:82-169): a reference QuadPotential object replaces init's mass matrix
     pot_var0 = pot_mean0 = None
@@ -222,6 +252,10 @@ def sample_b200_nuts(
     lo, hi = parallel.my_chain_range(chains)
     step_rngs, pot_rngs, jitter_seeds = brng.chain_generators(random_seed, chains)
     q0_all = initial_points(spec, chains, jitter_seeds, initvals, jitter, cm.logp_dlogp)
+    if init == "map" and potential is None:
+        q_map, cov = map_and_neg_hessian(cm, q0_all[0])
+        q0_all = np.broadcast_to(q_map, q0_all.shape).copy()  # initial_points = [start] * chains
+        cm.set_dense_mass(cov=cov)
     # init_nuts: mean start point over ALL chains as the estimator's prior mean (mcmc.py:1890-1894)
     mean0 = np.broadcast_to(q0_all.mean(axis=0) if pot_mean0 is None else pot_mean0, (hi - lo, spec.n)).copy()
     if pot_var0 is not None:

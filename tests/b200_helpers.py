@@ -123,6 +123,10 @@ class OracleEngine:
         self.spec, self.n = spec, spec.n
         self.f = logp_numpy.make_logp(spec)
 
+    def set_dense_mass(self, cov=None, *, inverse=None):
+        assert cov is not None, "the stand-in takes QuadPotentialFull(cov) only"
+        self.dense_cov = np.array(cov, dtype=np.float64)
+
     def logp_dlogp(self, q):
         q = np.asarray(q, dtype=np.float64).reshape(-1, self.n)
         out = [self.f(x) for x in q]
@@ -134,7 +138,8 @@ class OracleEngine:
         from oracle import nuts_numpy
         from pymc_b200.engine import NutsResult
 
-        assert mass in ("diag", "diag_adapt", "dense_adapt") and z is not None, "the stand-in draws momentum from the host stream only"
+        assert mass in ("diag", "diag_adapt", "dense_adapt", "dense") and z is not None, "the stand-in draws momentum from the host stream only"
+        self.last_q0 = np.array(q0, dtype=np.float64)
         q0 = np.asarray(q0, dtype=np.float64).reshape(-1, self.n)
         C, T = q0.shape[0], tune + draws
         qs_all, st_all = [], []
@@ -146,6 +151,8 @@ class OracleEngine:
                                               adaptation_window=unused.get("adaptation_window", 101))
             elif mass == "diag":  # QuadPotentialDiag(v)
                 m = nuts_numpy.DiagMass(v0, adapt=False)
+            elif mass == "dense":  # QuadPotentialFull(cov) from set_dense_mass
+                m = nuts_numpy.DenseMass(self.dense_cov)
             else:
                 m = nuts_numpy.DiagMass(v0, adapt=True, initial_mean=m0.copy(), initial_weight=mass_initial_weight,
                                         adaptation_window=unused.get("adaptation_window", 101),

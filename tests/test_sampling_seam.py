@@ -118,6 +118,25 @@ def test_log_likelihood_group_from_the_pointwise_pass():
         assert np.array_equal(res.posterior[k], plain.posterior[k])
 
 
+def test_init_map_starts_every_chain_at_the_optimum_with_the_negated_hessian():
+    """init="map" (mcmc.py:1981-1985): find_MAP by L-BFGS-B on the engine's logp/dlogp, cov = -Hessian (finite differences of
+    the gradient, one batched call), QuadPotentialFull(cov), initial_points = [map] * chains."""
+    spec = models.logistic(n_rows=200, n_features=4, seed=9)
+    X, y = spec.data["X"], spec.data["y"].astype(np.float64)
+    eng = OracleEngine(spec)
+    q, cov = sampling.map_and_neg_hessian(eng, spec.initial_point())
+    lp, g = eng.logp_dlogp(q[None])
+    assert np.max(np.abs(g[0])) <= 1e-4  # a stationary point of logp
+    p = 1.0 / (1.0 + np.exp(-(X @ q)))
+    want = X.T @ (X * (p * (1 - p))[:, None]) + np.eye(4)  # -Hessian of logp for beta ~ Normal(0, 1), Bernoulli-logit likelihood
+    np.testing.assert_allclose(cov, want, rtol=1e-6, atol=1e-8)
+    res = sampling.sample_b200_nuts(6, tune=10, chains=3, random_seed=2, model=eng, momentum="numpy", keep_untransformed=True,
+                                    init="map", compute_convergence_checks=False)
+    assert res.unconstrained.shape == (3, 6, 4)
+    assert np.allclose(eng.last_q0, np.broadcast_to(q, (3, 4)), rtol=0, atol=1e-12)  # every chain starts at the MAP
+    np.testing.assert_allclose(eng.dense_cov, want, rtol=1e-6, atol=1e-8)
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys

@@ -184,7 +184,9 @@ def sample_b200_nuts(
     ``init`` (pm.sample / init_nuts, pymc/sampling/mcmc.py:1759-2021): "auto" = "jitter+adapt_diag"; "adapt_diag";
     "jitter+adapt_diag_grad" (QuadPotentialDiagAdaptExp, alpha 0.02, stop at tune - 50 when tune > 250);
     "adapt_full" / "jitter+adapt_full" (QuadPotentialFullAdapt: a dense covariance per chain, identity start, weight 10,
-    mcmc.py:1986-2005); "map" (every chain starts at the L-BFGS-B optimum, QuadPotentialFull(-Hessian), mcmc.py:1981-1985).
+    mcmc.py:1986-2005); "map" (every chain starts at the L-BFGS-B optimum, QuadPotentialFull(-Hessian), mcmc.py:1981-1985);
+    "advi", "advi+adapt_diag", "advi_map" (mean-field ADVI on the engine's logp/dlogp, ``pymc_b200.advi``; ``nuts_kwargs["n_init"]``
+    caps its iterations, default 200000, mcmc.py:1913-1980).
     ``step``: "nuts" (target_accept default 0.8) or "hmc" (HamiltonianMC, default 0.65).
     ``momentum="numpy"`` draws the momentum normals from each chain's NumPy potential stream exactly like
     the reference (host-generated, uploaded); ``"device"`` generates them on the GPU (Philox).
@@ -225,9 +227,13 @@ def sample_b200_nuts(
         mass = "dense_adapt"  # QuadPotentialFullAdapt(n, mean, eye, 10): mcmc.py:1986-2005
     elif init == "map":
         mass = "dense"        # every chain starts at the MAP; QuadPotentialFull(-Hessian): mcmc.py:1981-1985 (resolved below)
+    elif init in ("advi", "advi_map"):
+        mass = "diag"         # QuadPotentialDiag(approx.std**2), start points drawn from the approximation: mcmc.py:1940-1980
+    elif init == "advi+adapt_diag":
+        mass = "diag_adapt"   # QuadPotentialDiagAdapt(n, approx.mean, approx.std**2, 50): mcmc.py:1913-1938
     else:
         raise ValueError(f"init={init!r}: implemented initialisations are (jitter+)adapt_diag, (jitter+)adapt_diag_grad, "
-                         "(jitter+)adapt_full and map")
+                         "(jitter+)adapt_full, map, advi, advi+adapt_diag and advi_map")
     mass = nk.pop("mass", mass)  # "dense": QuadPotentialFull with the model's covariance (MvNormal models)
     # pm.NUTS(potential=...) (hmc/base_hmc.py:82-169): a reference QuadPotential object replaces init's mass matrix
     pot_var0 = pot_mean0 = None
@@ -256,6 +262,19 @@ def sample_b200_nuts(
         q_map, cov = map_and_neg_hessian(cm, q0_all[0])
         q0_all = np.broadcast_to(q_map, q0_all.shape).copy()  # initial_points = [start] * chains
         cm.set_dense_mass(cov=cov)
+    advi_mean = None
+    if init.startswith("advi") and potential is None:
+        from . import advi
+
+        start = map_and_neg_hessian(cm, q0_all[0])[0] if init == "advi_map" else q0_all[0]  # MeanField(start=find_MAP())
+        seeds = np.random.SeedSequence(random_seed).spawn(2) if not isinstance(random_seed, np.random.Generator) else [random_seed] * 2
+        advi_mean, advi_std, advi_it = advi.fit_meanfield(cm.logp_dlogp, start, n=int(nk.pop("n_init", 200_000)), seed=seeds[0])
+        g = np.random.default_rng(seeds[1])
+        q0_all = advi_mean + advi_std * g.standard_normal((chains, spec.n))  # approx.sample(draws=chains)
+        pot_var0 = advi_std**2
+        if init == "advi+adapt_diag":
+            pot_mean0 = advi_mean
+            nk.setdefault("mass_initial_weight", 50.0)
     # init_nuts: mean start point over ALL chains as the estimator's prior mean (mcmc.py:1890-1894)
     mean0 = np.broadcast_to(q0_all.mean(axis=0) if pot_mean0 is None else pot_mean0, (hi - lo, spec.n)).copy()
     if pot_var0 is not None:

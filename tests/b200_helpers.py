@@ -140,6 +140,8 @@ class OracleEngine:
 
         assert mass in ("diag", "diag_adapt", "dense_adapt", "dense") and z is not None, "the stand-in draws momentum from the host stream only"
         self.last_q0 = np.array(q0, dtype=np.float64)
+        self.last_call = dict(mass=mass, var0=None if var0 is None else np.array(var0), mean0=None if mean0 is None else np.array(mean0),
+                              mass_initial_weight=mass_initial_weight)
         q0 = np.asarray(q0, dtype=np.float64).reshape(-1, self.n)
         C, T = q0.shape[0], tune + draws
         qs_all, st_all = [], []

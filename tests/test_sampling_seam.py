@@ -76,7 +76,7 @@ def test_init_adapt_full_hands_the_reference_potential_to_the_engine():
     import pytest
 
     with pytest.raises(ValueError, match="adapt_full"):
-        sampling.sample_b200_nuts(2, tune=2, chains=1, random_seed=1, model=OracleEngine(spec), momentum="numpy", init="advi")
+        sampling.sample_b200_nuts(2, tune=2, chains=1, random_seed=1, model=OracleEngine(spec), momentum="numpy", init="jitter+nope")
 
 
 def test_log_likelihood_group_from_the_pointwise_pass():
@@ -135,6 +135,39 @@ def test_init_map_starts_every_chain_at_the_optimum_with_the_negated_hessian():
     assert res.unconstrained.shape == (3, 6, 4)
     assert np.allclose(eng.last_q0, np.broadcast_to(q, (3, 4)), rtol=0, atol=1e-12)  # every chain starts at the MAP
     np.testing.assert_allclose(eng.dense_cov, want, rtol=1e-6, atol=1e-8)
+
+
+def test_advi_fit_and_the_advi_init_branches():
+    """pymc_b200.advi.fit_meanfield finds the mean / sd of a factorised Gaussian target with the reference's optimiser and
+    stopping rule; init="advi" -> QuadPotentialDiag(std**2) and start points drawn from the approximation,
+    init="advi+adapt_diag" -> QuadPotentialDiagAdapt(n, mean, std**2, 50) (mcmc.py:1913-1958)."""
+    from pymc_b200 import advi
+
+    m, sd = np.array([1.0, -2.0, 0.5, 3.0]), np.array([0.5, 2.0, 1.0, 0.25])
+
+    def f(q):
+        q = np.atleast_2d(q)
+        r = (q - m) / sd
+        return -0.5 * np.sum(r * r, axis=1), -(q - m) / sd**2
+
+    mu, s_, it = advi.fit_meanfield(f, np.zeros(4), seed=1)
+    assert 1000 < it < 200_000  # stopped by the parameter-convergence rule, not by the iteration cap
+    # the reference's stopping rule (parameters moved < 1e-2 in 100 iterations) ends the fit at optimiser-step accuracy
+    assert np.all(np.abs(mu - m) < 0.5) and np.all((s_ > 0.6 * sd) & (s_ < 2.0 * sd))
+    mu2, s2, it2 = advi.fit_meanfield(f, np.zeros(4), seed=1)
+    assert it2 == it and np.array_equal(mu2, mu) and np.array_equal(s2, s_)  # reproducible for a seed
+
+    spec = models.std_normal(5)
+    for init, kind, weight in (("advi", "diag", None), ("advi+adapt_diag", "diag_adapt", 50.0)):
+        eng = OracleEngine(spec)
+        res = sampling.sample_b200_nuts(5, tune=12, chains=3, random_seed=3, model=eng, momentum="numpy", keep_untransformed=True,
+                                        init=init, nuts_kwargs={"n_init": 4000}, compute_convergence_checks=False)
+        assert res.unconstrained.shape == (3, 5, 5) and eng.last_call["mass"] == kind
+        v0 = eng.last_call["var0"]
+        assert v0.shape == (3, 5) and np.all(v0 == v0[0]) and np.all((v0[0] > 0.3) & (v0[0] < 2.5))  # std**2 of N(0, 1), roughly
+        assert not np.array_equal(eng.last_q0[0], eng.last_q0[1])  # start points are draws of the approximation
+        if weight is not None:
+            assert eng.last_call["mass_initial_weight"] == weight and np.all(np.abs(eng.last_call["mean0"]) < 0.5)
 
 
 WORKER = textwrap.dedent(

@@ -71,6 +71,16 @@ def _const_value(x):
         return None
 
 
+def _static_size(x):
+    """Number of elements of a graph variable when its type says so (``x.type.shape`` all known), else None."""
+    shape = getattr(getattr(x, "type", None), "shape", None)
+    if shape is None:
+        shape = getattr(x, "static_shape", None)
+    if shape is None or any(d is None for d in shape):
+        return None
+    return int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+
+
 def from_pymc(model) -> _ir.ModelIR:
     import pymc as pm  # noqa: F401  (lazy: absent from the build image)
     from pytensor.tensor.elemwise import DimShuffle, Elemwise
@@ -278,6 +288,21 @@ def from_pymc(model) -> _ir.ModelIR:
         else:
             raise NotImplementedError(f"{rv.name}: likelihood {type(rv.owner.op).__name__} is outside the closed set "
                                       f"{sorted(_ir.LIK_DISTS)}")
-    out = _ir.ModelIR(vars_, priors, liks, ar1, name=getattr(model, "name", "") or "pymc_model")
+    # ---- pm.Deterministic: recorded in the posterior, never part of logp -------------------------------------------------
+    dets = []
+    for dv in getattr(model, "deterministics", []) or []:
+        size = _static_size(dv)
+        if size is None:
+            raise NotImplementedError(f"{dv.name}: the size of this Deterministic is not known statically")
+        expr = dv
+        if expr.owner is not None and type(expr.owner.op).__name__ in ("Identity", "Copy", "DeepCopyOp", "ViewOp") and \
+                len(expr.owner.inputs) == 1:
+            expr = expr.owner.inputs[0]  # pm.Deterministic wraps its expression in a named copy
+        terms = []
+        for c, f in terms_of(expr, size):
+            coef = None if (np.ndim(c) == 0 and float(c) == 1.0) else (np.asarray(c, dtype=np.float64) if np.ndim(c) else float(c))
+            terms.append(_ir.Term(list(f), coef))
+        dets.append(_ir.Deterministic(dv.name, size, terms))
+    out = _ir.ModelIR(vars_, priors, liks, ar1, name=getattr(model, "name", "") or "pymc_model", deterministics=dets)
     out.validate()
     return out

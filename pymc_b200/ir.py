@@ -96,6 +96,17 @@ class Likelihood:
 
 
 @dataclass
+class Deterministic:
+    """``pm.Deterministic(name, expr)`` whose expression is a linear predictor of the CONSTRAINED variables (the same closed form as
+    a likelihood's location): recorded in the posterior group like the reference's trace does (model/core.py:1956-2040,
+    backends/base.py:184-191), evaluated on the host from the draws -- it never enters logp."""
+
+    name: str
+    size: int
+    terms: list
+
+
+@dataclass
 class AR1:
     var: str
     phi: float | Ref = 1.0
@@ -110,6 +121,7 @@ class ModelIR:
     likelihoods: list = field(default_factory=list)
     ar1: list = field(default_factory=list)
     name: str = "model"
+    deterministics: list = field(default_factory=list)
 
     # ---- layout -----------------------------------------------------------------------------------------------------
     @property
@@ -198,6 +210,29 @@ class ModelIR:
                 s = 1.0 / (1.0 + np.exp(-x))
                 x = s * hi + (1.0 - s) * lo
             out[v.rv_name] = x[..., 0] if v.size == 1 else x
+        return out
+
+    def eval_deterministics(self, posterior: dict) -> dict:
+        """Deterministics from CONSTRAINED draws (``posterior``: rv name -> [..., size] or [...] for scalars, as ``constrain``
+        returns them): value_i = sum_t coef_t[i] * prod_f x_f[idx_f[i]]."""
+        out = {}
+        for d in self.deterministics:
+            lead = None
+            total = 0.0
+            for t in d.terms:
+                term = 1.0 if t.coef is None else np.asarray(t.coef, dtype=np.float64)
+                for vn, idx in t.factors:
+                    v = self.var(vn)
+                    x = np.asarray(posterior[v.rv_name])
+                    if v.size == 1:
+                        x = x[..., None]
+                    lead = x.shape[:-1]
+                    term = term * (x[..., np.asarray(idx)] if idx is not None else x)
+                total = total + term
+            total = np.asarray(total, dtype=np.float64)
+            if lead is not None:
+                total = np.broadcast_to(total, lead + (d.size,))
+            out[d.name] = total[..., 0] if d.size == 1 else total
         return out
 
     def observed_data(self) -> dict:

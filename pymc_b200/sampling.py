@@ -311,6 +311,9 @@ def sample_b200_nuts(
 
     def pack(dq, st):
         post = spec.split_rv(dq) if on_device else spec.constrain(dq)
+        ir_ = getattr(cm, "ir", None)
+        if ir_ is not None and getattr(ir_, "deterministics", None):  # pm.Deterministic values, from the constrained draws
+            post.update(ir_.eval_deterministics(post))
         if var_names is not None:
             post = {k: v for k, v in post.items() if k in var_names}
         stats = {_STAT_RENAME[k]: (v.astype(bool) if v.dtype == np.uint8 else v) for k, v in st.items()}

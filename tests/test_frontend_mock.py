@@ -274,6 +274,37 @@ def test_stochastic_volatility_graph_ar1_interval_and_log_variance_likelihood(fa
     _same_density(m, logp_numpy.make_logp(spec), spec.n, seed=3)
 
 
+def test_deterministics_are_lowered_and_evaluated_from_the_draws(fake_pytensor):
+    """pm.Deterministic("theta", mu + tau * theta_t): lowered to the same linear-predictor form, evaluated on the host from the
+    constrained draws, never part of logp."""
+    from pymc_b200 import from_pymc, models
+
+    spec = models.eight_schools()
+    M = FakeModel("eight_schools")
+    mu = M.free(rv("NormalRV", "mu", Constant(0.0), Constant(5.0)), 1)
+    tau = M.free(rv("HalfCauchyRV", "tau", Constant(0.0), Constant(5.0)), 1, LogTransform())
+    theta_t = M.free(rv("NormalRV", "theta_t", Constant(0.0), Constant(1.0)), 8)
+    loc = elem("Add", bcast(mu), elem("Mul", bcast(tau), theta_t))
+    M.observe(rv("NormalRV", "y", loc, Constant(spec.data["sigma"])), spec.data["y"])
+    theta = apply(type("Identity", (), {})(), loc, name="theta")
+    theta.type = types.SimpleNamespace(shape=(8,))
+    half = elem("TrueDiv", bcast(mu), Constant(2.0))
+    half.name, half.type = "half_mu", types.SimpleNamespace(shape=())
+    M.deterministics = [theta, half]
+    m = from_pymc(M)
+    assert [d.name for d in m.deterministics] == ["theta", "half_mu"] and [d.size for d in m.deterministics] == [8, 1]
+    q = m.initial_point() + np.random.default_rng(0).normal(size=(2, 3, m.n))
+    c = m.constrain(q)
+    d = m.eval_deterministics(c)
+    np.testing.assert_allclose(d["theta"], c["mu"][..., None] + c["tau"][..., None] * c["theta_t"], rtol=1e-14)
+    np.testing.assert_allclose(d["half_mu"], 0.5 * c["mu"], rtol=1e-14)
+    unknown = elem("Add", bcast(mu), theta_t)
+    unknown.name, unknown.type = "u", types.SimpleNamespace(shape=(None,))
+    M.deterministics = [unknown]
+    with pytest.raises(NotImplementedError, match="statically"):
+        from_pymc(M)
+
+
 def test_graphs_outside_the_closed_set_are_refused(fake_pytensor):
     from pymc_b200 import from_pymc
 

@@ -116,6 +116,12 @@ def test_log_likelihood_group_from_the_pointwise_pass():
     assert "log_likelihood" not in plain.groups()
     for k in res.posterior:  # asking for the group does not change the draws
         assert np.array_equal(res.posterior[k], plain.posterior[k])
+    # a Deterministic of the IR appears in the posterior group, computed from the constrained draws
+    m.deterministics.append(ir.Deterministic("a_scaled", m.var("a").size, [ir.Term([("sigma_a_log__", None), ("a", None)])]))
+    det = sampling.sample_b200_nuts(5, tune=8, chains=2, random_seed=4, model=IrStandIn(m), momentum="numpy",
+                                    compute_convergence_checks=False)
+    np.testing.assert_allclose(det.posterior["a_scaled"], det.posterior["sigma_a"][..., None] * det.posterior["a"], rtol=1e-14)
+    assert np.array_equal(det.posterior["a"], plain.posterior["a"])
 
 
 def test_init_map_starts_every_chain_at_the_optimum_with_the_negated_hessian():
